@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the Whisper-Tiny batched greedy transcription path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--chunks C] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the whole hot path (log-mel frontend -> conv stem -> encoder -> cross-K/V ->
+prefill + 195 greedy steps with fused logits+argmax) over C synthetic 30 s chunks per GPU
+(random-init Whisper-Tiny weights in the reference's file format).  Chunks are independent, so
+ranks shard them with no data-path collective (weak scaling: C per GPU); only the final gather of
+token ids crosses NVLink (NCCL all_gather), inside the timed region.
+
+  value  audio-seconds per second, whole job, PCM already resident in HBM, CUDA events on the stream
+  e2e    same through the public host API (Whisper.transcribe_pcm_batch) with pinned HOST pcm:
+         host->device copy of the pcm and device->host read of the tokens inside the timed region
+  roofline      decode cross-attention kernel (dominant): algorithmic K/V bytes / event-timed duration
+  cpu_baseline  oracle/ (CPU restatement of the reference) timed on this box's host cores, rank 0, N=1
+
+`--impl reference` times the reference's own algorithm on the host CPU (the Mojo binary cannot run
+here: Mach-O arm64, no Mojo toolchain -> the C restatement in oracle/ is used, kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio_sec_per_sec_whisper_tiny_batched_greedy"
+UNIT = "audio-s/s"
+CHUNK_SECONDS = 30.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chunks", type=int, default=2048, help="30 s chunks per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-chunks", type=int, default=4, help="chunks per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on host cores (oracle port)
+# ---------------------------------------------------------------------------------------------
+def cpu_transcribe_rate(n_chunks: int, repeats: int = 1):
+    """audio-s/s of the CPU restatement (all host threads via OpenMP), batch 1 like the reference."""
+    from oracle import oracle as O
+    from whisper_mojo_b200 import WhisperConfig, synth
+
+    cfg = WhisperConfig.tiny()
+    w = synth.make_weights(cfg, seed=0)
+    mel = synth.make_mel(n_chunks, cfg, 0)
+    om = O.OracleWhisper(cfg, w)
+    om.transcribe(mel[0])  # warm-up (mirrors benchmark_python.py:25-26)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        n_tok = 0
+        for i in range(n_chunks):
+            n_tok += len(om.transcribe(mel[i]))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_chunks * CHUNK_SECONDS / best, best, O.num_threads(), n_tok
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    for _ in range(max(args.warmup, 0)):
+        pass  # the CPU arm warms up inside cpu_transcribe_rate (one untimed transcribe per step)
+    times, rate = [], 0.0
+    cores = 1
+    for _ in range(max(args.steps, 1)):
+        rate, dt, cores, _ = cpu_transcribe_rate(args.cpu_chunks)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = args.cpu_chunks * CHUNK_SECONDS / (ms / 1e3)
+    sample = (f"{args.cpu_chunks} synthetic 30 s chunks per step, batch 1, precomputed log-mel "
+              f"(the reference's timed region, main.mojo:29-31), encoder + prefill + 195 greedy steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "whisper-tiny batched greedy transcription, 2048 x 30 s chunks per GPU",
+                   "reference_arm": "CPU restatement of whisper.Mojo (oracle/whisper_oracle.c); the shipped ./main is "
+                                    "Mach-O arm64 and no Mojo toolchain exists in this image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def synth_pcm_gpu(n, n_samples, device, seed):
+    """Synthetic 16 kHz audio made on the device: 0.1*N(0,1) + a sine sweep + a high tone, quiet tail."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, n_samples), dtype=torch.float32, device=device)
+    t = torch.arange(n_samples, device=device, dtype=torch.float32) / 16000.0
+    T = float(n_samples) / 16000.0
+    for i0 in range(0, n, 64):
+        i1 = min(n, i0 + 64)
+        k = torch.arange(i0, i1, device=device, dtype=torch.float32)[:, None]
+        f0, f1 = 100.0 + 50.0 * (k % 7), 3000.0 + 400.0 * (k % 5)
+        x = 0.1 * torch.randn((i1 - i0, n_samples), generator=g, device=device)
+        x += 0.5 * torch.sin(2 * np.pi * (f0 * t + 0.5 * (f1 - f0) / T * t * t))
+        x += 0.25 * torch.sin(2 * np.pi * (7000.0 - 100.0 * (k % 11)) * t)
+        x[:, int(n_samples * 0.8):] *= 1e-3
+        out[i0:i1] = x
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from whisper_mojo_b200 import WeightLoader, Whisper, WhisperConfig, _lib, synth
+    from whisper_mojo_b200.dist import gather_tokens
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = WhisperConfig.tiny()
+    C = args.chunks
+    stream = torch.cuda.current_stream()
+    model = Whisper(cfg, stream=stream.cuda_stream)
+    model.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
+    pcm = synth_pcm_gpu(C, cfg.n_samples, dev, seed=1234 + rank)  # 3.9 GB at C=2048: larger than the 126 MB L2
+    n_total = C * world
+
+    def step():
+        toks, lens = model.transcribe_pcm_batch(pcm)
+        if world > 1:
+            toks, lens = gather_tokens(toks, lens, n_total, dst=None)
+        return toks, lens
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        toks, lens = step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    phases = {"frontend_ms": 0.0, "encoder_ms": 0.0, "decode_ms": 0.0}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        toks, lens = step()
+        tm = model.last_timing()
+        for k in phases:
+            phases[k] += tm[k] / args.steps
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_total * CHUNK_SECONDS / (ms / 1e3)
+    mean_len = float(lens.float().mean().item())
+
+    # ---- end-to-end through the public host API: pinned host pcm in, host tokens out ----------
+    e2e = None
+    if not args.no_e2e:
+        pcm_host = torch.empty((C, cfg.n_samples), dtype=torch.float32, pin_memory=True)
+        pcm_host.copy_(pcm)
+        pcm_np = pcm_host.numpy()
+        model.transcribe_pcm_batch(pcm_np)  # warm-up of the host path
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            th, lh = model.transcribe_pcm_batch(pcm_np)  # H2D pcm + compute + D2H tokens, synchronous
+        sync_all()
+        dt = (time.perf_counter() - t0) / args.steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_total * CHUNK_SECONDS / dt, "unit": UNIT, "h2d_bytes_per_step": int(pcm_np.nbytes),
+               "d2h_bytes_per_step": int(th.nbytes + lh.nbytes), "ms_per_step": dt * 1e3,
+               "api": "Whisper.transcribe_pcm_batch (wm_transcribe_pcm)"}
+        del pcm_host
+
+    # ---- roofline of the dominant kernel: decode cross-attention, event-timed per launch -------
+    roofline = None
+    try:
+        model.set_option("profile_attn", 1)
+        model.transcribe_pcm_batch(pcm)
+        torch.cuda.synchronize()
+        tot_ms, n_launch = model.last_cross_attention_timing()
+        model.set_option("profile_attn", 0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # algorithmic bytes per launch: every chunk's cross K and V of one layer (bf16) read once,
+        # plus the query and output rows: B * (2*S*D + 2*D) * 2 bytes   (e_kv = 2)
+        alg = C * (2 * cfg.n_audio_ctx * cfg.d_model + 2 * cfg.d_model) * 2
+        if n_launch > 0:
+            avg_ms = tot_ms / n_launch
+            ach = alg / (avg_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "decode_attn_kernel (cross-attention, one layer, one step)",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s",
+                        "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": n_launch,
+                        "algorithmic_bytes_per_launch": alg,
+                        "share_of_decode": tot_ms / max(model.last_timing()["decode_ms"], 1e-9)}
+    except Exception as ex:  # never lose the headline number to the profiling pass
+        roofline = {"error": str(ex)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, dt, cores, _ = cpu_transcribe_rate(args.cpu_chunks)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_chunks} of the same synthetic-weight 30 s chunks, batch 1, precomputed log-mel "
+                         f"(reference's timed region), {dt:.1f} s of CPU work"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "whisper-tiny batched greedy transcription (BASELINE.json configs[3]): "
+                                   f"{C} synthetic 30 s chunks per GPU per step, pcm -> log-mel -> encoder -> "
+                                   "196 decoder forwards (EOT never fires with random weights)",
+                       "chunks_per_gpu": C, "global_chunks": n_total, "weights": "random-init whisper-tiny shapes, seed 0",
+                       "l2": "inputs (pcm %.1f GB per GPU) larger than L2; no explicit flush" % (pcm.numel() * 4 / 1e9),
+                       "parallelism": f"chunks sharded x{world}, no data-path collective, final NCCL all_gather of ids",
+                       "mean_tokens_per_chunk": mean_len},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "phases_ms_per_step": phases,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

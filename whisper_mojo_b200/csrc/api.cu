@@ -1,0 +1,691 @@
+// api.cu -- the C ABI declared in include/whisper_b200.h: handle tables, argument validation and
+// host<->device staging around model.cu / ops.cu.  No C++ type or exception crosses this file.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "model.h"
+#include "ops.h"
+
+namespace wb {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+struct TensorH {
+    float *data = nullptr;
+    int64_t rows = 0, cols = 0;
+    bool view = false;
+};
+
+static std::mutex g_mu;
+static std::unordered_map<uint64_t, TensorH *> g_tensors;
+static std::unordered_map<uint64_t, Model *> g_models;
+static std::unordered_map<uint64_t, Cache *> g_caches;
+static uint64_t g_next = 1;
+
+template <typename T>
+static uint64_t put(std::unordered_map<uint64_t, T *> &tab, T *p) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t h = g_next++;
+    tab[h] = p;
+    return h;
+}
+template <typename T>
+static T *get(std::unordered_map<uint64_t, T *> &tab, uint64_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = tab.find(h);
+    return it == tab.end() ? nullptr : it->second;
+}
+template <typename T>
+static T *take(std::unordered_map<uint64_t, T *> &tab, uint64_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = tab.find(h);
+    if (it == tab.end()) return nullptr;
+    T *p = it->second;
+    tab.erase(it);
+    return p;
+}
+
+static int need_device() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (libwhisper_b200 has no CPU fallback)");
+        return WB_ERR_CUDA;
+    }
+    return WB_OK;
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+#define TENSOR(var, h)                                  \
+    TensorH *var = get(g_tensors, h);                   \
+    WB_ARG(var != nullptr, "bad tensor handle %llu", (unsigned long long)(h))
+#define MODEL(var, h)                                  \
+    Model *var = get(g_models, h);                     \
+    WB_ARG(var != nullptr, "bad model handle %llu", (unsigned long long)(h))
+#define CACHE(var, h)                                  \
+    Cache *var = get(g_caches, h);                     \
+    WB_ARG(var != nullptr, "bad cache handle %llu", (unsigned long long)(h))
+
+extern "C" {
+
+int wb_last_error(char *buf, size_t n) {
+    if (!buf || n == 0) return WB_ERR_ARG;
+    snprintf(buf, n, "%s", g_err);
+    return WB_OK;
+}
+int wb_abi_version(void) { return 1; }
+int64_t wb_kernel_launch_count(void) { return g_launches.load(); }
+
+// ---- op level ----------------------------------------------------------------------------------
+
+int wt_tensor_alloc(int64_t rows, int64_t cols, wt_tensor *out) {
+    WB_ARG(out && rows >= 0 && cols >= 0, "tensor_alloc: bad shape");
+    WB_CHECK(need_device());
+    TensorH *t = new TensorH();
+    t->rows = rows, t->cols = cols;
+    size_t n = (size_t)rows * cols;
+    if (n) {
+        cudaError_t e = cudaMalloc((void **)&t->data, n * 4);
+        if (e == cudaSuccess) e = cudaMemset(t->data, 0, n * 4);  // whisper_tensor.mojo:23
+        if (e != cudaSuccess) {
+            set_error("tensor_alloc(%lld x %lld): %s", (long long)rows, (long long)cols, cudaGetErrorString(e));
+            delete t;
+            return WB_ERR_CUDA;
+        }
+    }
+    *out = put(g_tensors, t);
+    return WB_OK;
+}
+
+int wt_tensor_view(wt_tensor base, int64_t offset, int64_t rows, int64_t cols, wt_tensor *out) {
+    TENSOR(b, base);
+    WB_ARG(out && offset >= 0 && rows >= 0 && cols >= 0 && offset + rows * cols <= b->rows * b->cols,
+           "tensor_view: window outside the base tensor");
+    TensorH *t = new TensorH();
+    t->data = b->data + offset, t->rows = rows, t->cols = cols, t->view = true;
+    *out = put(g_tensors, t);
+    return WB_OK;
+}
+
+int wt_tensor_free(wt_tensor h) {
+    if (h == 0) return WB_OK;
+    TensorH *t = take(g_tensors, h);
+    WB_ARG(t != nullptr, "bad tensor handle %llu", (unsigned long long)h);
+    if (!t->view && t->data) cudaFree(t->data);
+    delete t;
+    return WB_OK;
+}
+
+int wt_tensor_shape(wt_tensor h, int64_t *rows, int64_t *cols) {
+    TENSOR(t, h);
+    if (rows) *rows = t->rows;
+    if (cols) *cols = t->cols;
+    return WB_OK;
+}
+
+int wt_tensor_data(wt_tensor h, void **dev_ptr) {
+    TENSOR(t, h);
+    WB_ARG(dev_ptr, "null out pointer");
+    *dev_ptr = t->data;
+    return WB_OK;
+}
+
+int wt_tensor_upload(wt_tensor h, int64_t offset, const float *host, int64_t n) {
+    TENSOR(t, h);
+    WB_ARG(host && offset >= 0 && n >= 0 && offset + n <= t->rows * t->cols, "tensor_upload: range outside tensor");
+    if (n) WB_CUDA(cudaMemcpy(t->data + offset, host, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return WB_OK;
+}
+
+int wt_tensor_download(wt_tensor h, int64_t offset, float *host, int64_t n) {
+    TENSOR(t, h);
+    WB_ARG(host && offset >= 0 && n >= 0 && offset + n <= t->rows * t->cols, "tensor_download: range outside tensor");
+    if (n) WB_CUDA(cudaMemcpy(host, t->data + offset, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return WB_OK;
+}
+
+int wt_tensor_copy(wt_tensor dst, int64_t dst_off, wt_tensor src, int64_t src_off, int64_t n) {
+    TENSOR(d, dst);
+    TENSOR(s, src);
+    WB_ARG(n >= 0 && dst_off >= 0 && src_off >= 0 && dst_off + n <= d->rows * d->cols &&
+               src_off + n <= s->rows * s->cols,
+           "tensor_copy: range outside tensor");
+    if (n) WB_CUDA(cudaMemcpy(d->data + dst_off, s->data + src_off, (size_t)n * 4, cudaMemcpyDeviceToDevice));
+    return WB_OK;
+}
+
+int wt_matmul(wt_tensor C, wt_tensor A, wt_tensor B, wt_tensor bias) {
+    TENSOR(c, C);
+    TENSOR(a, A);
+    TENSOR(b, B);
+    TensorH *bs = nullptr;
+    if (bias) {
+        bs = get(g_tensors, bias);
+        WB_ARG(bs != nullptr, "bad bias handle");
+        if (bs->rows * bs->cols == 0) bs = nullptr;  // Tensor(0,0) = no bias
+    }
+    WB_ARG(a->cols == b->cols && c->rows == a->rows && c->cols == b->rows,
+           "matmul: shapes C[%lld,%lld] A[%lld,%lld] B[%lld,%lld]", (long long)c->rows, (long long)c->cols,
+           (long long)a->rows, (long long)a->cols, (long long)b->rows, (long long)b->cols);
+    WB_ARG(!bs || bs->rows * bs->cols == b->rows, "matmul: bias length");
+    WB_CHECK(op_matmul(0, c->data, a->data, b->data, bs ? bs->data : nullptr, (int)a->rows, (int)b->rows, (int)a->cols));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+int wt_layer_norm(wt_tensor out, wt_tensor inp, wt_tensor gamma, wt_tensor beta, float eps) {
+    TENSOR(o, out);
+    TENSOR(x, inp);
+    TENSOR(g, gamma);
+    TENSOR(b, beta);
+    WB_ARG(o->rows == x->rows && o->cols == x->cols && g->rows * g->cols == x->cols && b->rows * b->cols == x->cols,
+           "layer_norm: shapes");
+    WB_CHECK(op_layer_norm(0, o->data, x->data, g->data, b->data, (int)x->rows, (int)x->cols, eps));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+int wt_gelu(wt_tensor h) {
+    TENSOR(t, h);
+    WB_CHECK(op_gelu(0, t->data, (size_t)(t->rows * t->cols)));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+int wt_softmax(wt_tensor h) {
+    TENSOR(t, h);
+    WB_CHECK(op_softmax(0, t->data, (int)t->rows, (int)t->cols));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+int wt_transpose_conv_weights(wt_tensor w, int C_out, int C_in, int K, wt_tensor *out) {
+    TENSOR(t, w);
+    WB_ARG(out && K == 3 && (int64_t)C_out * C_in * K == t->rows * t->cols, "transpose_conv_weights: shape");
+    wt_tensor nh = 0;
+    WB_CHECK(wt_tensor_alloc((int64_t)C_out * K, C_in, &nh));
+    TensorH *n = get(g_tensors, nh);
+    WB_CHECK(op_transpose_conv_weights(0, n->data, t->data, C_out, C_in, K));
+    WB_CUDA(cudaStreamSynchronize(0));
+    *out = nh;
+    return WB_OK;
+}
+
+int wt_conv1d(wt_tensor out, wt_tensor inp, wt_tensor weight, wt_tensor bias, int stride, int padding, int out_T) {
+    TENSOR(o, out);
+    TENSOR(x, inp);
+    TENSOR(w, weight);
+    TENSOR(b, bias);
+    WB_ARG(stride >= 1 && padding >= 0 && w->rows % 3 == 0 && w->cols == x->rows, "conv1d: weight / input shapes");
+    const int C_out = (int)(w->rows / 3), L_in = (int)x->cols, L_out = (L_in + 2 * padding - 3) / stride + 1;
+    WB_ARG(b->rows * b->cols == C_out, "conv1d: bias length");
+    WB_ARG(out_T ? (o->rows == L_out && o->cols == C_out) : (o->rows == C_out && o->cols == L_out),
+           "conv1d: output shape");
+    WB_CHECK(op_conv1d(0, o->data, x->data, w->data, b->data, (int)x->rows, L_in, C_out, stride, padding, out_T));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+int wt_argmax(wt_tensor h, int64_t *idx) {
+    TENSOR(t, h);
+    WB_ARG(idx && t->rows * t->cols > 0, "argmax: empty tensor");
+    long long *d = nullptr;
+    WB_CUDA(cudaMalloc((void **)&d, sizeof(long long)));
+    int rc = op_argmax(0, t->data, t->rows * t->cols, d);
+    long long v = 0;
+    if (rc == WB_OK && cudaMemcpy(&v, d, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("argmax: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = WB_ERR_CUDA;
+    }
+    cudaFree(d);
+    *idx = v;
+    return rc;
+}
+
+int wt_add(wt_tensor out, wt_tensor a, wt_tensor b) {
+    TENSOR(o, out);
+    TENSOR(x, a);
+    TENSOR(y, b);
+    const int64_t n = o->rows * o->cols;
+    WB_ARG(x->rows * x->cols == n && y->rows * y->cols == n, "add: sizes");
+    WB_CHECK(op_add(0, o->data, x->data, y->data, (size_t)n));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+int wt_scale_mask(wt_tensor scores, float scale, int mask, int64_t base) {
+    TENSOR(s, scores);
+    WB_CHECK(op_scale_mask(0, s->data, (int)s->rows, (int)s->cols, scale, mask, base));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+int wt_embed(wt_tensor out, wt_tensor token_emb, wt_tensor pos_emb, const int32_t *tokens, int n, int start_pos) {
+    TENSOR(o, out);
+    TENSOR(te, token_emb);
+    TENSOR(pe, pos_emb);
+    WB_ARG(tokens && n > 0 && o->rows == n && o->cols == te->cols && pe->cols == te->cols, "embed: shapes");
+    WB_ARG(start_pos >= 0 && start_pos + n <= pe->rows, "embed: positions %d..%d outside pos_emb", start_pos,
+           start_pos + n);
+    for (int i = 0; i < n; i++) WB_ARG(tokens[i] >= 0 && tokens[i] < te->rows, "embed: token id %d out of range", tokens[i]);
+    int *d = nullptr;
+    WB_CUDA(cudaMalloc((void **)&d, (size_t)n * 4));
+    int rc = WB_OK;
+    if (cudaMemcpy(d, tokens, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = WB_ERR_CUDA;
+    if (rc == WB_OK) rc = op_embed(0, o->data, te->data, pe->data, d, n, (int)te->cols, start_pos);
+    if (rc == WB_OK && cudaStreamSynchronize(0) != cudaSuccess) rc = WB_ERR_CUDA;
+    if (rc == WB_ERR_CUDA) set_error("embed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    return rc;
+}
+
+int wt_transpose(wt_tensor out, wt_tensor in) {
+    TENSOR(o, out);
+    TENSOR(x, in);
+    WB_ARG(o->rows == x->cols && o->cols == x->rows, "transpose: shapes");
+    WB_CHECK(op_transpose(0, o->data, x->data, (int)x->rows, (int)x->cols));
+    WB_CUDA(cudaStreamSynchronize(0));
+    return WB_OK;
+}
+
+// ---- model level -------------------------------------------------------------------------------
+
+int wm_create(const wm_config *cfg, void *stream, wm_model *out) {
+    WB_ARG(out, "wm_create: null out");
+    Model *m = nullptr;
+    WB_CHECK(model_create(cfg, stream, &m));
+    *out = put(g_models, m);
+    return WB_OK;
+}
+
+int wm_destroy(wm_model h) {
+    if (h == 0) return WB_OK;
+    Model *m = take(g_models, h);
+    WB_ARG(m != nullptr, "bad model handle");
+    model_destroy(m);
+    return WB_OK;
+}
+
+int64_t wm_weight_count(const wm_config *cfg) {
+    if (!cfg) return -1;
+    return make_layout(*cfg).total;
+}
+
+int wm_load_weights(wm_model h, const float *host, int64_t n_floats) {
+    MODEL(m, h);
+    return model_load(m, host, n_floats);
+}
+
+int wm_load_weights_file(wm_model h, const char *path) {
+    MODEL(m, h);
+    WB_ARG(path, "null path");
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_error("cannot open %s", path);
+        return WB_ERR_IO;
+    }
+    fseek(f, 0, SEEK_END);
+    long long bytes = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (bytes != m->lay.total * 4) {  // the reference never checks this (loader.mojo:21-27)
+        fclose(f);
+        set_error("%s has %lld bytes, config needs %lld", path, bytes, (long long)m->lay.total * 4);
+        return WB_ERR_IO;
+    }
+    float *buf = nullptr;
+    if (cudaMallocHost((void **)&buf, (size_t)bytes) != cudaSuccess) {
+        fclose(f);
+        set_error("cannot allocate %lld bytes of pinned memory", bytes);
+        return WB_ERR_CUDA;
+    }
+    size_t got = fread(buf, 1, (size_t)bytes, f);
+    fclose(f);
+    int rc = WB_OK;
+    if ((long long)got != bytes) {
+        set_error("short read on %s", path);
+        rc = WB_ERR_IO;
+    } else {
+        rc = model_load(m, buf, m->lay.total);
+    }
+    cudaFreeHost(buf);
+    return rc;
+}
+
+int wm_weight_tensor(wm_model h, int index, void **dev_ptr, int64_t *n_floats) {
+    MODEL(m, h);
+    WB_ARG(m->loaded, "weights not loaded");
+    WB_ARG(index >= 0 && index < (int)m->lay.tensors.size(), "weight tensor index %d out of range", index);
+    if (dev_ptr) *dev_ptr = m->w32 + m->lay.tensors[index].first;
+    if (n_floats) *n_floats = m->lay.tensors[index].second;
+    return WB_OK;
+}
+
+int wm_set_option(wm_model h, const char *key, int64_t value) {
+    MODEL(m, h);
+    WB_ARG(key, "null key");
+    if (!strcmp(key, "gemm_impl")) m->gemm_impl = (int)value;
+    else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
+    else if (!strcmp(key, "use_graph")) m->use_graph = (int)value;
+    else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
+    else if (!strcmp(key, "enc_batch")) {
+        WB_ARG(value >= 1 && value <= 4096, "enc_batch out of range");
+        m->enc_batch = (int)value;
+    } else if (!strcmp(key, "wave_max")) {
+        WB_ARG(value >= 1, "wave_max out of range");
+        m->wave_max = (int)value;
+    } else {
+        set_error("unknown option %s", key);
+        return WB_ERR_ARG;
+    }
+    return WB_OK;
+}
+
+}  // extern "C"
+
+// Stage a host array on the device, run `fn(dev_in, dev_out)`, copy the result back.
+template <typename Tin, typename Tout, typename Fn>
+static int staged(Model *m, const Tin *in_host, size_t n_in, Tout *out_host, size_t n_out, Fn fn) {
+    Tin *din = nullptr;
+    Tout *dout = nullptr;
+    int rc = WB_OK;
+    if (cudaMalloc((void **)&din, std::max<size_t>(n_in, 1) * sizeof(Tin)) != cudaSuccess ||
+        cudaMalloc((void **)&dout, std::max<size_t>(n_out, 1) * sizeof(Tout)) != cudaSuccess) {
+        set_error("staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = WB_ERR_CUDA;
+    }
+    if (rc == WB_OK && cudaMemcpyAsync(din, in_host, n_in * sizeof(Tin), cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
+        rc = WB_ERR_CUDA;
+    if (rc == WB_OK) rc = fn(din, dout);
+    if (rc == WB_OK &&
+        cudaMemcpyAsync(out_host, dout, n_out * sizeof(Tout), cudaMemcpyDeviceToHost, m->stream) != cudaSuccess)
+        rc = WB_ERR_CUDA;
+    if (rc == WB_OK && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = WB_ERR_CUDA;
+    if (rc == WB_ERR_CUDA && g_err[0] == 0) set_error("CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(din);
+    cudaFree(dout);
+    return rc;
+}
+
+extern "C" {
+
+int wm_logmel_dev(wm_model h, const float *pcm_dev, int n_chunks, float *mel_dev) {
+    MODEL(m, h);
+    WB_ARG(pcm_dev && mel_dev && n_chunks > 0, "logmel: bad arguments");
+    return model_logmel(m, pcm_dev, n_chunks, mel_dev);
+}
+int wm_logmel(wm_model h, const float *pcm_host, int n_chunks, float *mel_host) {
+    MODEL(m, h);
+    WB_ARG(pcm_host && mel_host && n_chunks > 0, "logmel: bad arguments");
+    g_err[0] = 0;
+    return staged(m, pcm_host, (size_t)n_chunks * m->n_samples, mel_host, (size_t)n_chunks * m->NM * m->n_frames,
+                  [&](const float *i, float *o) { return model_logmel(m, i, n_chunks, o); });
+}
+
+int wm_encode_dev(wm_model h, const float *mel_dev, int n_chunks, float *enc_out_dev) {
+    MODEL(m, h);
+    WB_ARG(mel_dev && enc_out_dev && n_chunks > 0, "encode: bad arguments");
+    return model_encode(m, mel_dev, n_chunks, enc_out_dev, nullptr, 0);
+}
+int wm_encode(wm_model h, const float *mel_host, int n_chunks, float *enc_out_host) {
+    MODEL(m, h);
+    WB_ARG(mel_host && enc_out_host && n_chunks > 0, "encode: bad arguments");
+    g_err[0] = 0;
+    return staged(m, mel_host, (size_t)n_chunks * m->NM * m->n_frames, enc_out_host, (size_t)n_chunks * m->S * m->D,
+                  [&](const float *i, float *o) { return model_encode(m, i, n_chunks, o, nullptr, 0); });
+}
+
+int wm_kvcache_create(wm_model h, int n_chunks, int max_len, wm_cache *out) {
+    MODEL(m, h);
+    WB_ARG(out, "kvcache_create: null out");
+    Cache *c = nullptr;
+    WB_CHECK(cache_create(m, n_chunks, max_len, true, &c));
+    *out = put(g_caches, c);
+    return WB_OK;
+}
+int wm_kvcache_destroy(wm_cache h) {
+    if (h == 0) return WB_OK;
+    Cache *c = take(g_caches, h);
+    WB_ARG(c != nullptr, "bad cache handle");
+    cache_destroy(c);
+    return WB_OK;
+}
+int wm_kvcache_reset(wm_cache h) {
+    CACHE(c, h);
+    return cache_reset(c);
+}
+int wm_kvcache_len(wm_cache h, int *current_len) {
+    CACHE(c, h);
+    WB_ARG(current_len, "null out");
+    *current_len = c->host_len;
+    return WB_OK;
+}
+int wm_kvcache_set_encoder_dev(wm_model mh, wm_cache h, const float *enc_out_dev) {
+    MODEL(m, mh);
+    CACHE(c, h);
+    WB_ARG(c->m == m && enc_out_dev, "kvcache_set_encoder: cache belongs to another model / null input");
+    return cache_set_encoder(c, enc_out_dev);
+}
+
+int wm_decode_step(wm_model mh, wm_cache h, const int32_t *tokens_host, int start_pos, float *logits_host,
+                   int32_t *next_host) {
+    MODEL(m, mh);
+    CACHE(c, h);
+    WB_ARG(c->m == m, "decode_step: cache belongs to another model");
+    if (tokens_host)
+        for (int b = 0; b < c->B; b++)
+            WB_ARG(tokens_host[b] >= 0 && tokens_host[b] < m->V, "decode_step: token id %d out of range", tokens_host[b]);
+    return cache_step_api(c, tokens_host, start_pos, logits_host, next_host);
+}
+
+int wm_transcribe_dev(wm_model h, const float *mel_dev, int n_chunks, int32_t *out_tokens_dev, int32_t *out_len_dev) {
+    MODEL(m, h);
+    return model_transcribe(m, mel_dev, nullptr, n_chunks, out_tokens_dev, out_len_dev);
+}
+int wm_transcribe_pcm_dev(wm_model h, const float *pcm_dev, int n_chunks, int32_t *out_tokens_dev,
+                          int32_t *out_len_dev) {
+    MODEL(m, h);
+    return model_transcribe(m, nullptr, pcm_dev, n_chunks, out_tokens_dev, out_len_dev);
+}
+
+}  // extern "C"
+
+static int transcribe_host(Model *m, const float *in_host, bool pcm, int n, int32_t *out_tokens_host,
+                           int32_t *out_len_host) {
+    WB_ARG(in_host && out_tokens_host && out_len_host && n > 0, "transcribe: bad arguments");
+    g_err[0] = 0;
+    const int T_out = 5 + m->cfg.max_iters;
+    const size_t n_in = (size_t)n * (pcm ? (size_t)m->n_samples : (size_t)m->NM * m->n_frames);
+    // tokens and lengths share one staging buffer: [n*T_out tokens][n lengths]
+    std::vector<int32_t> tmp((size_t)n * T_out + n);
+    int rc = staged(m, in_host, n_in, tmp.data(), tmp.size(), [&](const float *i, int32_t *o) {
+        return model_transcribe(m, pcm ? nullptr : i, pcm ? i : nullptr, n, o, o + (size_t)n * T_out);
+    });
+    if (rc == WB_OK) {
+        memcpy(out_tokens_host, tmp.data(), (size_t)n * T_out * 4);
+        memcpy(out_len_host, tmp.data() + (size_t)n * T_out, (size_t)n * 4);
+    }
+    return rc;
+}
+
+extern "C" {
+
+int wm_transcribe(wm_model h, const float *mel_host, int n_chunks, int32_t *out_tokens_host, int32_t *out_len_host) {
+    MODEL(m, h);
+    return transcribe_host(m, mel_host, false, n_chunks, out_tokens_host, out_len_host);
+}
+int wm_transcribe_pcm(wm_model h, const float *pcm_host, int n_chunks, int32_t *out_tokens_host,
+                      int32_t *out_len_host) {
+    MODEL(m, h);
+    return transcribe_host(m, pcm_host, true, n_chunks, out_tokens_host, out_len_host);
+}
+
+int wm_teacher_forced(wm_model h, const float *enc_out_dev, int n_chunks, const int32_t *forced_host, int n_forced,
+                      float *logits_host) {
+    MODEL(m, h);
+    if (forced_host && n_chunks > 0 && n_forced > 0)
+        for (size_t i = 0; i < (size_t)n_chunks * n_forced; i++)
+            WB_ARG(forced_host[i] >= 0 && forced_host[i] < m->V, "teacher_forced: token id %d out of range",
+                   forced_host[i]);
+    return model_teacher_forced(m, enc_out_dev, n_chunks, forced_host, n_forced, logits_host);
+}
+
+int wm_last_timing(wm_model h, float ms[5]) {
+    MODEL(m, h);
+    WB_ARG(ms, "null out");
+    for (int i = 0; i < 5; i++) ms[i] = m->timing[i];
+    return WB_OK;
+}
+
+int wm_last_kernel_timing(wm_model h, const char *kernel, float *total_ms, int64_t *launches) {
+    MODEL(m, h);
+    WB_ARG(kernel && !strcmp(kernel, "cross_attention"), "only \"cross_attention\" is instrumented");
+    if (total_ms) *total_ms = m->cross_timer.total_ms;
+    if (launches) *launches = m->cross_timer.launches;
+    return WB_OK;
+}
+
+
+static __global__ void bf16_to_f32_kernel(const __nv_bfloat16 *src, float *dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+int wb_debug_gemm(int impl, const float *A_host, int batches, int src_rows, int lda, int Cin, int taps,
+                  int conv_stride, int pad, int rows_per_batch, const float *W_host, int N, const float *bias_host,
+                  int epi, float *out_host) {
+    WB_ARG(A_host && W_host && out_host && batches > 0 && src_rows > 0 && rows_per_batch > 0 && N > 0,
+           "debug_gemm: bad arguments");
+    WB_CHECK(need_device());
+    const size_t nA = (size_t)batches * src_rows * lda, K = (size_t)taps * Cin, nW = (size_t)N * K;
+    const size_t M = (size_t)batches * rows_per_batch, nO = M * N;
+    const int tiles_n = gemm_tiles_n(N);
+    float *dA32 = nullptr, *dW32 = nullptr, *dbias = nullptr, *dout = nullptr, *dpv = nullptr;
+    __nv_bfloat16 *dA = nullptr, *dW = nullptr, *dob = nullptr;
+    int *dpi = nullptr, *dnext = nullptr;
+    int rc = WB_OK;
+    auto ok = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == WB_OK) {
+            set_error("debug_gemm: %s", cudaGetErrorString(e));
+            rc = WB_ERR_CUDA;
+        }
+    };
+    ok(cudaMalloc((void **)&dA32, nA * 4));
+    ok(cudaMalloc((void **)&dW32, nW * 4));
+    ok(cudaMalloc((void **)&dA, nA * 2));
+    ok(cudaMalloc((void **)&dW, nW * 2));
+    ok(cudaMalloc((void **)&dbias, (size_t)N * 4));
+    ok(cudaMalloc((void **)&dout, nO * 4));
+    ok(cudaMalloc((void **)&dob, nO * 2));
+    ok(cudaMalloc((void **)&dpv, M * tiles_n * 4));
+    ok(cudaMalloc((void **)&dpi, M * tiles_n * 4));
+    ok(cudaMalloc((void **)&dnext, M * 4));
+    if (rc == WB_OK) {
+        ok(cudaMemcpy(dA32, A_host, nA * 4, cudaMemcpyHostToDevice));
+        ok(cudaMemcpy(dW32, W_host, nW * 4, cudaMemcpyHostToDevice));
+        if (bias_host) ok(cudaMemcpy(dbias, bias_host, (size_t)N * 4, cudaMemcpyHostToDevice));
+        ok(cudaMemcpy(dout, out_host, nO * 4, cudaMemcpyHostToDevice));
+    }
+    if (rc == WB_OK) rc = convert_f32_bf16(0, dA32, dA, nA);
+    if (rc == WB_OK) rc = convert_f32_bf16(0, dW32, dW, nW);
+    if (rc == WB_OK) {
+        GemmDesc g;
+        g.A = dA, g.a_batch_stride = (int64_t)src_rows * lda, g.lda = lda, g.src_rows = src_rows;
+        g.conv_stride = conv_stride, g.pad = pad, g.taps = taps, g.Cin = Cin;
+        g.batches = batches, g.rows_per_batch = rows_per_batch;
+        g.W = dW, g.N = N, g.bias = bias_host ? dbias : nullptr, g.epi = epi;
+        const bool bf = (epi == EPI_STORE_BF16 || epi == EPI_GELU_BF16);
+        g.out[0] = bf ? (void *)dob : (void *)dout, g.out_ld[0] = N;
+        if (epi == EPI_ARGMAX) g.part_val = dpv, g.part_idx = dpi, g.logits = dout, g.out[0] = nullptr;
+        rc = gemm_run(0, g, impl);
+        if (rc == WB_OK && epi == EPI_ARGMAX) rc = argmax_partials(0, dpv, dpi, (int)M, tiles_n, dnext);
+        if (rc == WB_OK && bf) {
+            bf16_to_f32_kernel<<<(unsigned)((nO + 255) / 256), 256>>>(dob, dout, nO);
+            ok(cudaGetLastError());
+        }
+    }
+    if (rc == WB_OK) ok(cudaDeviceSynchronize());
+    if (rc == WB_OK) {
+        if (epi == EPI_ARGMAX) {
+            std::vector<int> nx(M);
+            ok(cudaMemcpy(nx.data(), dnext, M * 4, cudaMemcpyDeviceToHost));
+            ok(cudaMemcpy(out_host, dout, nO * 4, cudaMemcpyDeviceToHost));  // logits, then overwrite [row][0]? no:
+            // keep the logits intact; indices are returned in the LAST column slot of each row when N > 1
+            for (size_t r = 0; r < M; r++) out_host[r * N + (N - 1)] = (float)nx[r];
+        } else {
+            ok(cudaMemcpy(out_host, dout, nO * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    cudaFree(dA32), cudaFree(dW32), cudaFree(dA), cudaFree(dW), cudaFree(dbias), cudaFree(dout), cudaFree(dob);
+    cudaFree(dpv), cudaFree(dpi), cudaFree(dnext);
+    return rc;
+}
+
+
+int wb_debug_decode_attention(const float *q_host, const float *K_host, const float *V_host, int B, int H, int len,
+                              int splits, float *out_host) {
+    WB_ARG(q_host && K_host && V_host && out_host && B > 0 && H > 0 && len > 0 && splits > 0, "debug_attn: bad args");
+    WB_CHECK(need_device());
+    const int D = H * 64;
+    const size_t nq = (size_t)B * D, nkv = (size_t)B * len * D;
+    float *f32 = nullptr, *ws = nullptr;
+    __nv_bfloat16 *q = nullptr, *K = nullptr, *V = nullptr, *o = nullptr;
+    int *len_dev = nullptr;
+    int rc = WB_OK;
+    auto ok = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == WB_OK) {
+            set_error("debug_attn: %s", cudaGetErrorString(e));
+            rc = WB_ERR_CUDA;
+        }
+    };
+    ok(cudaMalloc((void **)&f32, nkv * 4));
+    ok(cudaMalloc((void **)&q, nq * 2));
+    ok(cudaMalloc((void **)&K, nkv * 2));
+    ok(cudaMalloc((void **)&V, nkv * 2));
+    ok(cudaMalloc((void **)&o, nq * 2));
+    ok(cudaMalloc((void **)&ws, (size_t)B * splits * H * 66 * 4));
+    ok(cudaMalloc((void **)&len_dev, 4));
+    const float *srcs[3] = {q_host, K_host, V_host};
+    __nv_bfloat16 *dsts[3] = {q, K, V};
+    const size_t ns[3] = {nq, nkv, nkv};
+    for (int i = 0; i < 3 && rc == WB_OK; i++) {
+        ok(cudaMemcpy(f32, srcs[i], ns[i] * 4, cudaMemcpyHostToDevice));
+        if (rc == WB_OK) rc = convert_f32_bf16(0, f32, dsts[i], ns[i]);
+        ok(cudaDeviceSynchronize());
+    }
+    if (rc == WB_OK) {
+        int lm1 = len - 1;
+        ok(cudaMemcpy(len_dev, &lm1, 4, cudaMemcpyHostToDevice));
+        DecodeAttnArgs a;
+        a.q = q, a.K = K, a.V = V, a.out = o, a.kv_batch_stride = (int64_t)len * D;
+        a.B = B, a.H = H, a.D = D, a.max_len = len, a.splits = splits, a.ws = ws;
+        // splits == 1 exercises the device-side length (self-attention), otherwise the constant one
+        if (splits == 1) a.len_const = 0, a.len_dev = len_dev, a.len_add = 1;
+        else a.len_const = len, a.len_dev = nullptr, a.len_add = 0;
+        rc = decode_attention(0, a);
+    }
+    if (rc == WB_OK) {
+        bf16_to_f32_kernel<<<(unsigned)((nq + 255) / 256), 256>>>(o, f32, nq);
+        ok(cudaGetLastError());
+        ok(cudaMemcpy(out_host, f32, nq * 4, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(f32), cudaFree(q), cudaFree(K), cudaFree(V), cudaFree(o), cudaFree(ws), cudaFree(len_dev);
+    return rc;
+}
+
+}  // extern "C"

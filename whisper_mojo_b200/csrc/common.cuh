@@ -1,0 +1,89 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libwhisper_b200.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/whisper_b200.h"
+
+namespace wb {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define WB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            wb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+            return WB_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define WB_CHECK(call)                 \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != WB_OK) return rc__; \
+    } while (0)
+
+#define WB_ARG(cond, ...)               \
+    do {                                \
+        if (!(cond)) {                  \
+            wb::set_error(__VA_ARGS__); \
+            return WB_ERR_ARG;          \
+        }                               \
+    } while (0)
+
+// Call after every <<<>>> launch: counts the launch and surfaces configuration errors.
+#define WB_LAUNCHED()                                                                              \
+    do {                                                                                           \
+        wb::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+        cudaError_t e__ = cudaPeekAtLastError();                                                   \
+        if (e__ != cudaSuccess) {                                                                  \
+            wb::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return WB_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers ------------------------------------------------------------------------
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// tanh GELU exactly as whisper_tensor.mojo:288-308 writes it (constants truncated as there).
+__device__ __forceinline__ float gelu_ref(float x) {
+    const float k0 = 0.79788456f, k1 = 0.044715f;
+    float x3 = x * x * x;
+    float inner = k0 * (x + k1 * x3);
+    return 0.5f * x * (1.0f + tanhf(inner));
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4 &v, float *f) {
+    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 t = __bfloat1622float2(p[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+}  // namespace wb

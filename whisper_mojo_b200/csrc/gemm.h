@@ -1,0 +1,64 @@
+// gemm.h -- bf16 tensor-core GEMM C = A * W^T (+bias) with fused epilogues, sm_100a.
+//
+// One kernel family serves every dense contraction of the path: the conv stem as an implicit GEMM
+// over 3 shifted taps (whisper_tensor.mojo:367-428), the encoder / decoder projections and MLPs
+// (the reference's matmul / MAX wrappers, whisper_tensor.mojo:74-246), the all-layer cross-K/V
+// projection (layers.mojo:148-157) and the tied-embedding logit projection fused with argmax
+// (whisper.mojo:159-166 + whisper_tensor.mojo:431-439).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wb {
+
+enum GemmEpi {
+    EPI_STORE_BF16 = 0,    // out_bf16 = acc + bias
+    EPI_GELU_BF16 = 1,     // out_bf16 = gelu(acc + bias)
+    EPI_RESID_F32 = 2,     // out_f32 += acc + bias               (residual add in place)
+    EPI_STORE_F32 = 3,     // out_f32 = acc + bias
+    EPI_ARGMAX = 4,        // per-row (max, first index) over each 128-column tile -> partials; optional f32 logits
+    EPI_GELU_POS_F32 = 5,  // out_f32 = gelu(acc + bias) + pos[row_in_batch][n]   (conv2 + positional add)
+};
+
+enum GemmImpl { GEMM_IMPL_REF = 0, GEMM_IMPL_TC = 1 };
+
+// Host-side description of one GEMM.
+//   A(b, m, tap*Cin + ci) = src[b*a_batch_stride + (m*conv_stride + tap - pad)*lda + ci]
+//   (zero when the source row is outside [0, src_rows)); plain GEMM: taps=1, conv_stride=1, pad=0.
+//   Output row index = b*rows_per_batch + m.
+struct GemmDesc {
+    const __nv_bfloat16 *A = nullptr;
+    int64_t a_batch_stride = 0;
+    int lda = 0, src_rows = 0, conv_stride = 1, pad = 0, taps = 1, Cin = 0;
+    int batches = 1, rows_per_batch = 0;
+    const __nv_bfloat16 *W = nullptr;  // [N][taps*Cin]
+    int N = 0;
+    const float *bias = nullptr;
+    int epi = EPI_STORE_BF16;
+    // Output routing.  Columns are split in segments of seg_cols (a multiple of 128, or N).
+    // n_seg_ptrs > 0: segment s writes to out[s] with row stride out_ld[s] (+ dyn offset).
+    // n_seg_ptrs == 0: segment s writes to out[0] + s*seg_stride with row stride out_ld[0].
+    void *out[3] = {nullptr, nullptr, nullptr};
+    int64_t out_ld[3] = {0, 0, 0};
+    int64_t seg_stride = 0;
+    int seg_cols = 0;  // 0 -> N
+    int n_seg_ptrs = 1;
+    const int *dyn_off = nullptr;  // device int; element offset added = (*dyn_off) * dyn_mult[s]
+    int64_t dyn_mult[3] = {0, 0, 0};
+    const float *pos = nullptr;  // EPI_GELU_POS_F32: [rows_per_batch][N]
+    float *part_val = nullptr;   // EPI_ARGMAX: [M][tiles_n]
+    int *part_idx = nullptr;
+    float *logits = nullptr;  // EPI_ARGMAX: optional full logits [M][N]
+};
+
+static inline int gemm_tiles_n(int N) { return (N + 127) / 128; }
+
+int gemm_run(cudaStream_t st, const GemmDesc &d, int impl);
+
+// Reduce the EPI_ARGMAX partials: next[b] = first index of the row maximum.
+int argmax_partials(cudaStream_t st, const float *part_val, const int *part_idx, int M, int tiles_n, int *next_dev);
+// Bring-up helper: build the same partials from full logits [M][N].
+int argmax_partials_from_logits(cudaStream_t st, const float *logits, int M, int N, float *part_val, int *part_idx);
+
+}  // namespace wb

@@ -1,0 +1,431 @@
+// kernels.cu -- LayerNorm, embedding, single-query (decode) attention, bring-up encoder attention and
+// greedy-loop bookkeeping for the batched fast path.  All HBM-bound: coalesced 128-bit accesses,
+// warp-shuffle reductions, no atomics in value-producing reductions (results do not depend on batch
+// size or position in the batch).
+#include "kernels.h"
+
+#include "common.cuh"
+
+namespace wb {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm fp32 -> bf16: one warp per row.
+// ---------------------------------------------------------------------------------------------
+template <bool EMBED>
+__global__ void __launch_bounds__(256) ln_bf16_kernel(const float *__restrict__ x_in, const float *__restrict__ gamma,
+                                                      const float *__restrict__ beta, int rows, int D,
+                                                      __nv_bfloat16 *__restrict__ out_bf16,
+                                                      float *__restrict__ out_f32,
+                                                      // EMBED only:
+                                                      const float *__restrict__ tok_emb,
+                                                      const float *__restrict__ pos_emb,
+                                                      const int *__restrict__ cur_tok, const int *__restrict__ pos_dev,
+                                                      int vocab, int n_pos, float *__restrict__ x_out) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    // D is a multiple of 128 for every supported config (heads * 64 with an even head count);
+    // up to 8 float4 per lane (D <= 1024) are kept in registers.
+    float4 v[8];
+    const int nvec = D >> 7;
+    float s = 0.f, q = 0.f;
+    if (EMBED) {
+        int tok = cur_tok[row];
+        tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+        int pos = *pos_dev;
+        pos = pos < 0 ? 0 : (pos >= n_pos ? n_pos - 1 : pos);
+        const float4 *te = reinterpret_cast<const float4 *>(tok_emb + (size_t)tok * D);
+        const float4 *pe = reinterpret_cast<const float4 *>(pos_emb + (size_t)pos * D);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < nvec) {
+                float4 a = te[i * 32 + lane], b = pe[i * 32 + lane];
+                v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+                reinterpret_cast<float4 *>(x_out + (size_t)row * D)[i * 32 + lane] = v[i];
+            }
+    } else {
+        const float4 *xr = reinterpret_cast<const float4 *>(x_in + (size_t)row * D);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < nvec) v[i] = xr[i * 32 + lane];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < nvec) {
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+            q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    const float mean = s / (float)D;
+    const float var = q / (float)D - mean * mean;
+    const float inv_std = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < nvec) {
+            float4 g = reinterpret_cast<const float4 *>(gamma)[i * 32 + lane];
+            float4 b = reinterpret_cast<const float4 *>(beta)[i * 32 + lane];
+            float4 r;
+            r.x = (v[i].x - mean) * inv_std * g.x + b.x;
+            r.y = (v[i].y - mean) * inv_std * g.y + b.y;
+            r.z = (v[i].z - mean) * inv_std * g.z + b.z;
+            r.w = (v[i].w - mean) * inv_std * g.w + b.w;
+            uint2 pk;
+            pk.x = pack_bf16x2(r.x, r.y);
+            pk.y = pack_bf16x2(r.z, r.w);
+            reinterpret_cast<uint2 *>(out_bf16 + (size_t)row * D)[i * 32 + lane] = pk;
+            if (out_f32) reinterpret_cast<float4 *>(out_f32 + (size_t)row * D)[i * 32 + lane] = r;
+        }
+}
+
+int ln_bf16(cudaStream_t st, const float *x, const float *gamma, const float *beta, int rows, int D,
+            __nv_bfloat16 *out_bf16, float *out_f32) {
+    WB_ARG(D % 128 == 0 && D <= 1024, "ln_bf16: D=%d must be a multiple of 128 and <= 1024", D);
+    if (rows <= 0) return WB_OK;
+    ln_bf16_kernel<false><<<cdiv(rows, 8), 256, 0, st>>>(x, gamma, beta, rows, D, out_bf16, out_f32, nullptr, nullptr,
+                                                          nullptr, nullptr, 0, 0, nullptr);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const int *cur_tok, const int *pos_dev,
+             int B, int D, int vocab, int n_pos, const float *gamma, const float *beta, float *x,
+             __nv_bfloat16 *xn) {
+    WB_ARG(D % 128 == 0 && D <= 1024, "embed_ln: D=%d must be a multiple of 128 and <= 1024", D);
+    if (B <= 0) return WB_OK;
+    ln_bf16_kernel<true><<<cdiv(B, 8), 256, 0, st>>>(nullptr, gamma, beta, B, D, xn, nullptr, tok_emb, pos_emb,
+                                                      cur_tok, pos_dev, vocab, n_pos, x);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode attention: grid (B, splits), one warp per head.  Lane layout inside a warp: 4 key rows x
+// 8 lanes, each lane owning 8 of the 64 head dims (one 128-bit load); a key row's head slice is one
+// full 128-byte line, and the H warps of a CTA walk the same rows, so a CTA streams whole K / V rows.
+// Three phases as in the reference (scores -> softmax -> weighted sum); scores live in shared memory.
+// ---------------------------------------------------------------------------------------------
+struct DecodeAttnDev {
+    const __nv_bfloat16 *q, *K, *V;
+    __nv_bfloat16 *out;
+    long long kv_batch_stride;
+    int H, D, len_const, len_add, splits, smem_len;
+    const int *len_dev;
+    float *ws;
+};
+
+__device__ __forceinline__ uint4 ld_stream(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p) {
+    extern __shared__ float s_scores[];  // [H][smem_len]
+    const int b = blockIdx.x, split = blockIdx.y;
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = lane & 7, sub = lane >> 3;
+    const int len = p.len_dev ? (*p.len_dev + p.len_add) : p.len_const;
+    int chunk = (len + p.splits - 1) / p.splits;
+    chunk = (chunk + 3) & ~3;
+    const int j0 = split * chunk;
+    const int j1 = min(len, j0 + chunk);
+    const int n = max(j1 - j0, 0);
+    float *sc = s_scores + (size_t)h * p.smem_len;
+
+    float qf[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4 *>(p.q + (size_t)b * p.D + h * 64 + c * 8), qf);
+    const float scale = 0.125f;  // 1/sqrt(head_dim), head_dim = 64 (layers.mojo:184)
+    const __nv_bfloat16 *Kb = p.K + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
+    const __nv_bfloat16 *Vb = p.V + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
+
+    // phase 1: scores
+    float m = -1e10f;  // layers.mojo:188
+    for (int i0 = 0; i0 < n; i0 += 16) {  // warp-uniform trip count: the shuffles below need all 32 lanes
+        const int i = i0 + sub;
+        uint4 kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int jj = i + 4 * u;
+            kv[u] = (jj < n) ? ld_stream(Kb + (size_t)(j0 + jj) * p.D) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float kf[8];
+            bf16x8_to_float(kv[u], kf);
+            float d = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; t++) d += qf[t] * kf[t];
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            int jj = i + 4 * u;
+            if (jj < n) {
+                float s = d * scale;
+                m = fmaxf(m, s);
+                if (c == 0) sc[jj] = s;
+            }
+        }
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    __syncwarp();
+    // phase 2: exp and sum
+    float l = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        float e = __expf(sc[j] - m);
+        sc[j] = e;
+        l += e;
+    }
+    l = warp_sum(l);
+    __syncwarp();
+    // phase 3: weighted sum of V
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i0 = 0; i0 < n; i0 += 16) {
+        const int i = i0 + sub;
+        uint4 vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int jj = i + 4 * u;
+            vv[u] = (jj < n) ? ld_stream(Vb + (size_t)(j0 + jj) * p.D) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int jj = i + 4 * u;
+            float pj = (jj < n) ? sc[jj] : 0.f;
+            float vf[8];
+            bf16x8_to_float(vv[u], vf);
+#pragma unroll
+            for (int t = 0; t < 8; t++) acc[t] += pj * vf[t];
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 8);
+        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 16);
+    }
+    if (p.splits == 1) {
+        if (sub == 0) {
+            const float inv = 1.0f / l;
+            uint4 o;
+            o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+            o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+            o.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+            o.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+            *reinterpret_cast<uint4 *>(p.out + (size_t)b * p.D + h * 64 + c * 8) = o;
+        }
+    } else {
+        float *w = p.ws + (((size_t)b * p.splits + split) * p.H + h) * 66;
+        if (sub == 0) {
+#pragma unroll
+            for (int t = 0; t < 8; t++) w[c * 8 + t] = acc[t];
+            if (c == 0) w[64] = m, w[65] = l;
+        }
+    }
+}
+
+// Merge split-K partials: one warp per (b, h); lane owns 2 head dims.
+__global__ void decode_attn_combine_kernel(const float *__restrict__ ws, __nv_bfloat16 *__restrict__ out, int B, int H,
+                                           int D, int splits) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= B * H) return;
+    int b = w / H, h = w % H;
+    float m = -1e10f;
+    for (int s = 0; s < splits; s++) m = fmaxf(m, ws[(((size_t)b * splits + s) * H + h) * 66 + 64]);
+    float l = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int s = 0; s < splits; s++) {
+        const float *p = ws + (((size_t)b * splits + s) * H + h) * 66;
+        float f = __expf(p[64] - m);
+        l += p[65] * f;
+        o0 += p[2 * lane] * f;
+        o1 += p[2 * lane + 1] * f;
+    }
+    float inv = 1.0f / l;
+    *reinterpret_cast<uint32_t *>(out + (size_t)b * D + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+}
+
+int decode_attention_splits(int B, int len) {
+    int want = (592 + B - 1) / B;
+    int cap = len / 128;
+    if (cap < 1) cap = 1;
+    int s = want < cap ? want : cap;
+    return s < 1 ? 1 : s;
+}
+
+int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {
+    WB_ARG(a.H >= 1 && a.H <= 12 && a.D == a.H * 64, "decode_attention: H=%d D=%d unsupported", a.H, a.D);
+    WB_ARG(a.splits >= 1 && (a.splits == 1 || a.ws), "decode_attention: splits need a workspace");
+    if (a.B <= 0) return WB_OK;
+    DecodeAttnDev p;
+    p.q = a.q, p.K = a.K, p.V = a.V, p.out = a.out;
+    p.kv_batch_stride = a.kv_batch_stride;
+    p.H = a.H, p.D = a.D, p.len_const = a.len_const, p.len_add = a.len_add, p.splits = a.splits;
+    p.len_dev = a.len_dev, p.ws = a.ws;
+    int chunk = (a.max_len + a.splits - 1) / a.splits;
+    p.smem_len = ((chunk + 3) & ~3) + 4;
+    size_t smem = (size_t)a.H * p.smem_len * sizeof(float);
+    static size_t smem_opted = 48 * 1024;
+    if (smem > smem_opted) {
+        WB_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_opted = smem;
+    }
+    dim3 grid(a.B, a.splits);
+    decode_attn_kernel<<<grid, a.H * 32, smem, st>>>(p);
+    WB_LAUNCHED();
+    if (a.splits > 1) {
+        decode_attn_combine_kernel<<<cdiv(a.B * a.H, 8), 256, 0, st>>>(a.ws, a.out, a.B, a.H, a.D, a.splits);
+        WB_LAUNCHED();
+    }
+    return WB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Encoder attention, bring-up version: one warp per query row, scores in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) encoder_attn_ref_kernel(const __nv_bfloat16 *__restrict__ qkv,
+                                                               __nv_bfloat16 *__restrict__ out, int S, int H, int D) {
+    extern __shared__ float s_sc[];  // [8][S]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * 8 + warp, h = blockIdx.y, b = blockIdx.z;
+    if (qi >= S) return;
+    float *sc = s_sc + (size_t)warp * S;
+    const size_t ld = 3 * (size_t)D;
+    const __nv_bfloat16 *base = qkv + (size_t)b * S * ld;
+    float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(base + (size_t)qi * ld + h * 64 + 2 * lane));
+    float m = -INFINITY;
+    for (int j = 0; j < S; j++) {
+        float2 kv = __bfloat1622float2(
+            *reinterpret_cast<const __nv_bfloat162 *>(base + (size_t)j * ld + D + h * 64 + 2 * lane));
+        float d = warp_sum(qv.x * kv.x + qv.y * kv.y) * 0.125f;
+        m = fmaxf(m, d);
+        if (lane == 0) sc[j] = d;
+    }
+    __syncwarp();
+    float l = 0.f;
+    for (int j = lane; j < S; j += 32) {
+        float e = expf(sc[j] - m);
+        sc[j] = e;
+        l += e;
+    }
+    l = warp_sum(l);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < S; j++) {
+        float2 vv = __bfloat1622float2(
+            *reinterpret_cast<const __nv_bfloat162 *>(base + (size_t)j * ld + 2 * D + h * 64 + 2 * lane));
+        float pj = sc[j];
+        o0 += pj * vv.x;
+        o1 += pj * vv.y;
+    }
+    float inv = 1.0f / l;
+    *reinterpret_cast<uint32_t *>(out + ((size_t)b * S + qi) * D + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+}
+
+int encoder_attention_ref(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D) {
+    if (B <= 0) return WB_OK;
+    size_t smem = (size_t)8 * S * sizeof(float);
+    static size_t smem_opted = 48 * 1024;
+    if (smem > smem_opted) {
+        WB_CUDA(cudaFuncSetAttribute(encoder_attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_opted = smem;
+    }
+    dim3 grid(cdiv(S, 8), H, B);
+    encoder_attn_ref_kernel<<<grid, 256, smem, st>>>(qkv, out, S, H, D);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Greedy-loop bookkeeping
+// ---------------------------------------------------------------------------------------------
+__global__ void greedy_init_kernel(GreedyState g, int B, int p0, int p1, int p2, int p3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) g.scalars[0] = 0, g.scalars[1] = 0, g.scalars[2] = 0;
+    if (i >= B) return;
+    int *row = g.tokens_out + (size_t)i * g.T_out;
+    for (int t = 0; t < g.T_out; t++) row[t] = -1;
+    row[0] = p0, row[1] = p1, row[2] = p2, row[3] = p3;
+    g.out_len[i] = 4;
+    g.cur_tok[i] = p0;
+    g.done[i] = 0;
+}
+int greedy_init(cudaStream_t st, const GreedyState &g, int B, const int *prompt) {
+    greedy_init_kernel<<<cdiv(B, 256), 256, 0, st>>>(g, B, prompt[0], prompt[1], prompt[2], prompt[3]);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+// Scalars are read by every thread before any thread of block 0 rewrites them at the end of the
+// NEXT launch; within this launch only thread 0 of block 0 writes them, after computing from the
+// values all threads would read -- other threads use only per-row state, so there is no race.
+__global__ void greedy_advance_kernel(GreedyState g, int B, int mode, int next_prompt_token,
+                                      const int *__restrict__ next) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        if (mode == 0) {
+            g.cur_tok[i] = next_prompt_token;
+        } else {
+            int tok = next[i];
+            if (!g.done[i]) {
+                int n = g.out_len[i];
+                if (n < g.T_out) {
+                    g.tokens_out[(size_t)i * g.T_out + n] = tok;
+                    g.out_len[i] = n + 1;
+                }
+                if (tok == g.eot) {
+                    g.done[i] = 1;
+                    atomicAdd(&g.scalars[2], 1);
+                }
+            }
+            g.cur_tok[i] = tok;
+        }
+    }
+    if (i == 0) {
+        int cl = g.scalars[0] + 1;
+        g.scalars[0] = cl;
+        // prefill tokens sit at positions 0..3; generated tokens use current_len - quirk (whisper.mojo:217)
+        g.scalars[1] = (mode == 0) ? cl : cl - g.pos_quirk;
+    }
+}
+int greedy_advance(cudaStream_t st, const GreedyState &g, int B, int mode, int next_prompt_token, const int *next) {
+    greedy_advance_kernel<<<cdiv(B, 256), 256, 0, st>>>(g, B, mode, next_prompt_token, next);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight conversion
+// ---------------------------------------------------------------------------------------------
+__global__ void convert_f32_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = __float2bfloat16(src[i]);
+}
+int convert_f32_bf16(cudaStream_t st, const float *src, __nv_bfloat16 *dst, size_t n) {
+    if (!n) return WB_OK;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    convert_f32_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+__global__ void convert_conv_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ dst, int C_out,
+                                           int C_in, int C_in_pad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)C_out * 3 * C_in_pad;
+    if (i >= n) return;
+    int ci = (int)(i % C_in_pad);
+    int k = (int)((i / C_in_pad) % 3);
+    int co = (int)(i / ((size_t)3 * C_in_pad));
+    float v = ci < C_in ? w[((size_t)co * C_in + ci) * 3 + k] : 0.f;
+    dst[i] = __float2bfloat16(v);
+}
+int convert_conv_weight(cudaStream_t st, const float *w, __nv_bfloat16 *dst, int C_out, int C_in, int C_in_pad) {
+    size_t n = (size_t)C_out * 3 * C_in_pad;
+    convert_conv_weight_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, dst, C_out, C_in, C_in_pad);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+}  // namespace wb

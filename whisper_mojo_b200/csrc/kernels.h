@@ -1,0 +1,82 @@
+// kernels.h -- launchers for the non-GEMM kernels of the batched fast path (kernels.cu, frontend.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wb {
+
+// LayerNorm (whisper_tensor.mojo:249-285, one-pass variance) fp32 in -> bf16 out (+ optional fp32 out).
+int ln_bf16(cudaStream_t st, const float *x, const float *gamma, const float *beta, int rows, int D,
+            __nv_bfloat16 *out_bf16, float *out_f32);
+
+// Decoder input (whisper.mojo:138-149) fused with the first LayerNorm of layer 0:
+//   x[b] = token_emb[cur_tok[b]] + pos_emb[*pos];  xn[b] = LN(x[b]) in bf16.
+int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const int *cur_tok, const int *pos_dev,
+             int B, int D, int vocab, int n_pos, const float *gamma, const float *beta, float *x,
+             __nv_bfloat16 *xn);
+
+// Single-query attention for one decode step (layers.mojo:186-272), batched over chunks and heads.
+//   q   bf16 [B][D]                         (head h = columns h*64 .. h*64+63)
+//   K,V bf16 [B][rows][D], chunk stride `kv_batch_stride` elements
+//   len = len_const, or *len_dev + len_add when len_dev != nullptr
+//   out bf16 [B][D]
+// `ws` is scratch for the split-K partials: floats [B][splits][H][66].
+struct DecodeAttnArgs {
+    const __nv_bfloat16 *q, *K, *V;
+    __nv_bfloat16 *out;
+    int64_t kv_batch_stride;
+    int B, H, D;
+    int len_const;
+    const int *len_dev;
+    int len_add;
+    int max_len;  // upper bound of len (sizes shared memory)
+    int splits;
+    float *ws;
+};
+int decode_attention(cudaStream_t st, const DecodeAttnArgs &a);
+int decode_attention_splits(int B, int len);
+
+// Encoder self-attention, bring-up implementation on CUDA cores (layers.mojo:273-342, no mask):
+// qkv bf16 [B*S][3D] -> out bf16 [B*S][D].
+int encoder_attention_ref(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D);
+
+// Greedy bookkeeping after a logits step (whisper.mojo:198-221): append next token unless the chunk
+// has finished, mark EOT, set the next input token, advance cur_len / pos.
+struct GreedyState {
+    int *tokens_out;  // [B][T_out], -1 filled
+    int *out_len;     // [B]
+    int *cur_tok;     // [B]
+    int *done;        // [B]
+    int *scalars;     // [0]=cur_len, [1]=pos, [2]=n_done
+    int T_out, eot, pos_quirk;
+};
+int greedy_init(cudaStream_t st, const GreedyState &g, int B, const int *prompt4_host);
+// mode 0: prefill advance (feed prompt[next_prompt_idx] next); mode 1: greedy append from `next`.
+int greedy_advance(cudaStream_t st, const GreedyState &g, int B, int mode, int next_prompt_token, const int *next);
+
+// ---- frontend (frontend.cu) ------------------------------------------------------------------
+struct FrontendTables {
+    float *tw_cos = nullptr, *tw_sin = nullptr;  // [200][104] twiddles cos/sin(2*pi*k*n/400), k < 101
+    float *window = nullptr;                     // [400] periodic Hann
+    float *mel_w = nullptr;                      // sparse filterbank weights
+    int *mel_start = nullptr, *mel_len = nullptr, *mel_off = nullptr;  // per mel bin
+    int n_mels = 0;
+};
+int frontend_tables_create(FrontendTables *t, int n_mels);
+void frontend_tables_destroy(FrontendTables *t);
+// pcm f32 [B][n_frames*160] -> raw log10 mel f32 [B][n_mels][n_frames] and per-chunk max (ordered-int encoded).
+int logmel_raw(cudaStream_t st, const FrontendTables &t, const float *pcm, int B, int n_frames, float *mel_raw,
+               int *chunk_max_enc);
+// Finalise in place: v = (max(v, chunk_max - 8) + 4) / 4.
+int logmel_finalize(cudaStream_t st, float *mel, const int *chunk_max_enc, int B, int n_mels, int n_frames);
+// mel f32 [B][n_mels][n_frames] -> bf16 [B][n_frames][128] (channels >= n_mels zero) for the conv1 GEMM.
+int mel_to_bf16_T(cudaStream_t st, const float *mel, __nv_bfloat16 *out, int B, int n_mels, int n_frames);
+
+// fp32 -> bf16 conversion helpers used at weight load.
+int convert_f32_bf16(cudaStream_t st, const float *src, __nv_bfloat16 *dst, size_t n);
+// conv weight [C_out][C_in][3] fp32 -> bf16 [C_out][3*C_in_pad] in the (tap, ci) order of
+// transpose_conv_weights (whisper_tensor.mojo:358-364), channels padded with zeros to C_in_pad.
+int convert_conv_weight(cudaStream_t st, const float *w, __nv_bfloat16 *dst, int C_out, int C_in, int C_in_pad);
+
+}  // namespace wb

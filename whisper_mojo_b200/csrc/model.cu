@@ -1,0 +1,633 @@
+// model.cu -- batched Whisper fast path: weight upload, encoder, cross-K/V, KV-cached greedy decode.
+//
+// Mirrors whisper.mojo (Whisper / WhisperEncoder / WhisperDecoder), layers.mojo
+// (ResidualAttentionBlock, MultiHeadAttention, KVCache) and loader.mojo, restructured for a batch of
+// independent 30 s chunks resident in HBM:
+//   * weights: the flat fp32 file image is uploaded once; bf16 copies of every matrix are made on
+//     the device (q/k/v fused into one [3D, D] matrix, the L cross-attention K/V projections fused
+//     into one [L*2*D, D] matrix, conv weights in the (tap, channel) order of transpose_conv_weights).
+//   * activations: fp32 residual stream, bf16 GEMM operands, fp32 accumulation.
+//   * KV cache: bf16, [layer][k|v][chunk][position][D] -- a chunk's K (or V) rows are contiguous so
+//     the decode attention kernels stream whole rows.
+//   * decode: one step = ~48 small kernels; cur_len / position / tokens / EOT flags live in device
+//     memory so a single CUDA graph of the step is replayed for the whole greedy loop.
+#include "model.h"
+
+#include <algorithm>
+#include <cstring>
+#include <type_traits>
+
+#include "common.cuh"
+#include "gemm.h"
+
+namespace wb {
+
+// ---------------------------------------------------------------------------------------------
+// layout of the flat weight file (export_weights.py:19-90; read order whisper.mojo:60-69,122-128)
+// ---------------------------------------------------------------------------------------------
+Layout make_layout(const wm_config &c) {
+    Layout l;
+    int64_t off = 0;
+    const int64_t D = c.d_model, F = 4 * D;
+    auto take = [&](int64_t n) {
+        int64_t o = off;
+        l.tensors.push_back({o, n});
+        off += n;
+        return o;
+    };
+    auto attn = [&](AttnW &a) {
+        a.q_w = take(D * D), a.q_b = take(D), a.k_w = take(D * D), a.v_w = take(D * D), a.v_b = take(D);
+        a.o_w = take(D * D), a.o_b = take(D);
+    };
+    auto block = [&](BlockW &b, bool dec) {
+        attn(b.attn);
+        b.attn_ln_w = take(D), b.attn_ln_b = take(D);
+        if (dec) {
+            attn(b.cross);
+            b.cross_ln_w = take(D), b.cross_ln_b = take(D);
+        }
+        b.fc1_w = take(F * D), b.fc1_b = take(F), b.fc2_w = take(D * F), b.fc2_b = take(D);
+        b.mlp_ln_w = take(D), b.mlp_ln_b = take(D);
+    };
+    l.conv1_w = take(D * c.n_mels * 3), l.conv1_b = take(D);
+    l.conv2_w = take(D * D * 3), l.conv2_b = take(D);
+    l.enc_pos = take((int64_t)c.n_audio_ctx * D);
+    l.enc.resize(c.n_layers);
+    for (auto &b : l.enc) block(b, false);
+    l.enc_ln_w = take(D), l.enc_ln_b = take(D);
+    l.tok_emb = take((int64_t)c.vocab_size * D);
+    l.dec_pos = take((int64_t)c.n_text_ctx * D);
+    l.dec.resize(c.n_layers);
+    for (auto &b : l.dec) block(b, true);
+    l.dec_ln_w = take(D), l.dec_ln_b = take(D);
+    l.total = off;
+    return l;
+}
+
+template <typename T>
+static int dalloc(Model *m, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e));
+        return WB_ERR_CUDA;
+    }
+    *p = reinterpret_cast<T *>(q);
+    if (m) m->owned.push_back(q);
+    return WB_OK;
+}
+
+int model_create(const wm_config *cfg, void *stream, Model **out) {
+    WB_ARG(cfg && out, "wm_create: null argument");
+    WB_ARG(cfg->d_model > 0 && cfg->n_heads > 0 && cfg->d_model == cfg->n_heads * 64,
+           "wm_create: head_dim must be 64 (d_model=%d n_heads=%d)", cfg->d_model, cfg->n_heads);
+    WB_ARG(cfg->d_model % 128 == 0 && cfg->d_model <= 1024, "wm_create: d_model must be a multiple of 128, <= 1024");
+    WB_ARG(cfg->n_mels > 0 && cfg->n_mels <= 128 && cfg->n_layers > 0 && cfg->vocab_size > 0 &&
+               cfg->n_audio_ctx > 0 && cfg->n_text_ctx >= 8 && cfg->max_iters >= 0,
+           "wm_create: bad config");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("wm_create: no CUDA device (this library has no CPU fallback)");
+        return WB_ERR_CUDA;
+    }
+    Model *m = new Model();
+    m->cfg = *cfg;
+    m->D = cfg->d_model, m->H = cfg->n_heads, m->L = cfg->n_layers, m->V = cfg->vocab_size;
+    m->S = cfg->n_audio_ctx, m->T = cfg->n_text_ctx, m->NM = cfg->n_mels, m->F = 4 * cfg->d_model;
+    m->n_frames = 2 * m->S, m->n_samples = m->n_frames * 160;
+    m->lay = make_layout(*cfg);
+    if (stream) {
+        m->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
+            delete m;
+            return WB_ERR_CUDA;
+        }
+        m->own_stream = true;
+    }
+    int rc = frontend_tables_create(&m->ft, m->NM);
+    if (rc != WB_OK) {
+        model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return WB_OK;
+}
+
+void model_destroy(Model *m) {
+    if (!m) return;
+    cudaStreamSynchronize(m->stream);
+    for (void *p : m->owned) cudaFree(p);
+    for (cudaEvent_t e : m->cross_timer.ev) cudaEventDestroy(e);
+    frontend_tables_destroy(&m->ft);
+    if (m->own_stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+// Whisper.load (whisper.mojo:180-182) + WeightLoader (loader.mojo): one upload, device-side repack.
+int model_load(Model *m, const float *host, int64_t n_floats) {
+    WB_ARG(host, "wm_load_weights: null pointer");
+    if (n_floats != m->lay.total) {
+        set_error("weight image has %lld fp32 values, config needs %lld", (long long)n_floats,
+                  (long long)m->lay.total);
+        return WB_ERR_IO;
+    }
+    WB_ARG(!m->loaded, "weights already loaded");
+    cudaStream_t st = m->stream;
+    const int D = m->D, L = m->L, F = m->F;
+    WB_CHECK(dalloc(m, &m->w32, (size_t)n_floats));
+    WB_CUDA(cudaMemcpyAsync(m->w32, host, (size_t)n_floats * 4, cudaMemcpyHostToDevice, st));
+    const float *W = m->w32;
+    const Layout &ly = m->lay;
+    WB_CHECK(dalloc(m, &m->conv1_w, (size_t)D * 3 * 128));
+    WB_CHECK(dalloc(m, &m->conv2_w, (size_t)D * 3 * D));
+    WB_CHECK(convert_conv_weight(st, W + ly.conv1_w, m->conv1_w, D, m->NM, 128));
+    WB_CHECK(convert_conv_weight(st, W + ly.conv2_w, m->conv2_w, D, D, D));
+    WB_CHECK(dalloc(m, &m->tok_emb_bf16, (size_t)m->V * D));
+    WB_CHECK(convert_f32_bf16(st, W + ly.tok_emb, m->tok_emb_bf16, (size_t)m->V * D));
+    WB_CHECK(dalloc(m, &m->cross_wkv, (size_t)L * 2 * D * D));
+    WB_CHECK(dalloc(m, &m->cross_bkv, (size_t)L * 2 * D));
+    WB_CUDA(cudaMemsetAsync(m->cross_bkv, 0, (size_t)L * 2 * D * 4, st));
+    m->enc.resize(L);
+    m->dec.resize(L);
+    const size_t DD = (size_t)D * D;
+    for (int side = 0; side < 2; side++) {
+        for (int i = 0; i < L; i++) {
+            const BlockW &b = side ? ly.dec[i] : ly.enc[i];
+            LayerDev &d = side ? m->dec[i] : m->enc[i];
+            WB_CHECK(dalloc(m, &d.wqkv, 3 * DD));
+            WB_CHECK(convert_f32_bf16(st, W + b.attn.q_w, d.wqkv, DD));
+            WB_CHECK(convert_f32_bf16(st, W + b.attn.k_w, d.wqkv + DD, DD));
+            WB_CHECK(convert_f32_bf16(st, W + b.attn.v_w, d.wqkv + 2 * DD, DD));
+            WB_CHECK(dalloc(m, &d.bqkv, (size_t)3 * D));
+            WB_CUDA(cudaMemsetAsync(d.bqkv, 0, (size_t)3 * D * 4, st));
+            WB_CUDA(cudaMemcpyAsync(d.bqkv, W + b.attn.q_b, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+            WB_CUDA(cudaMemcpyAsync(d.bqkv + 2 * D, W + b.attn.v_b, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+            WB_CHECK(dalloc(m, &d.wo, DD));
+            WB_CHECK(convert_f32_bf16(st, W + b.attn.o_w, d.wo, DD));
+            d.bo = W + b.attn.o_b;
+            WB_CHECK(dalloc(m, &d.w1, (size_t)F * D));
+            WB_CHECK(convert_f32_bf16(st, W + b.fc1_w, d.w1, (size_t)F * D));
+            WB_CHECK(dalloc(m, &d.w2, (size_t)F * D));
+            WB_CHECK(convert_f32_bf16(st, W + b.fc2_w, d.w2, (size_t)F * D));
+            d.b1 = W + b.fc1_b, d.b2 = W + b.fc2_b;
+            d.ln1_g = W + b.attn_ln_w, d.ln1_b = W + b.attn_ln_b;
+            d.ln3_g = W + b.mlp_ln_w, d.ln3_b = W + b.mlp_ln_b;
+            d.ln2_g = d.ln2_b = d.cbq = d.cbo = nullptr;
+            if (side) {
+                WB_CHECK(dalloc(m, &d.cwq, DD));
+                WB_CHECK(convert_f32_bf16(st, W + b.cross.q_w, d.cwq, DD));
+                WB_CHECK(dalloc(m, &d.cwo, DD));
+                WB_CHECK(convert_f32_bf16(st, W + b.cross.o_w, d.cwo, DD));
+                d.cbq = W + b.cross.q_b, d.cbo = W + b.cross.o_b;
+                d.ln2_g = W + b.cross_ln_w, d.ln2_b = W + b.cross_ln_b;
+                // fused cross K/V projection: rows [(i*2+0)*D, +D) = Wk (no bias), [(i*2+1)*D, +D) = Wv (+bias)
+                WB_CHECK(convert_f32_bf16(st, W + b.cross.k_w, m->cross_wkv + (size_t)(i * 2) * DD, DD));
+                WB_CHECK(convert_f32_bf16(st, W + b.cross.v_w, m->cross_wkv + (size_t)(i * 2 + 1) * DD, DD));
+                WB_CUDA(cudaMemcpyAsync(m->cross_bkv + (size_t)(i * 2 + 1) * D, W + b.cross.v_b, (size_t)D * 4,
+                                        cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    WB_CUDA(cudaStreamSynchronize(st));
+    m->loaded = true;
+    return WB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frontend
+// ---------------------------------------------------------------------------------------------
+int model_logmel(Model *m, const float *pcm_dev, int n, float *mel_dev) {
+    if (n <= 0) return WB_OK;
+    int *cmax = nullptr;
+    WB_CUDA(cudaMallocAsync((void **)&cmax, (size_t)n * sizeof(int), m->stream));
+    int rc = logmel_raw(m->stream, m->ft, pcm_dev, n, m->n_frames, mel_dev, cmax);
+    if (rc == WB_OK) rc = logmel_finalize(m->stream, mel_dev, cmax, n, m->NM, m->n_frames);
+    cudaFreeAsync(cmax, m->stream);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoder (whisper.mojo:71-99) + cross-K/V projection (layers.mojo:148-157)
+// ---------------------------------------------------------------------------------------------
+static int ensure_encoder_ws(Model *m, int n) {
+    if (n <= m->enc_cap) return WB_OK;
+    // (re)allocate; old buffers stay owned by the model and are freed at destroy -- the capacity only
+    // grows to enc_batch, so this happens at most a couple of times.
+    const size_t M = (size_t)n * m->S, D = m->D;
+    WB_CHECK(dalloc(m, &m->e_melT, (size_t)n * m->n_frames * 128));
+    WB_CHECK(dalloc(m, &m->e_x1T, (size_t)n * m->n_frames * D));
+    WB_CHECK(dalloc(m, &m->e_x, M * D));
+    WB_CHECK(dalloc(m, &m->e_xn, M * D));
+    WB_CHECK(dalloc(m, &m->e_qkv, M * 3 * D));
+    WB_CHECK(dalloc(m, &m->e_attn, M * D));
+    WB_CHECK(dalloc(m, &m->e_h, M * m->F));
+    WB_CHECK(dalloc(m, &m->e_enc, M * D));
+    m->enc_cap = n;
+    return WB_OK;
+}
+
+static GemmDesc plain_gemm(const bf16 *A, int M, int K, const bf16 *W, int N, const float *bias, int epi, void *out,
+                           int64_t out_ld) {
+    GemmDesc g;
+    g.A = A, g.lda = K, g.src_rows = M, g.Cin = K, g.rows_per_batch = M, g.batches = 1;
+    g.W = W, g.N = N, g.bias = bias, g.epi = epi;
+    g.out[0] = out, g.out_ld[0] = out_ld, g.n_seg_ptrs = 1;
+    return g;
+}
+
+static int cross_kv_project(Model *m, const bf16 *enc_bf16, int n, Cache *c, int cache_off) {
+    // out layout [L][2][B][S][D]; segment s = l*2+kv has stride B*S*D, rows are (chunk, position).
+    GemmDesc g = plain_gemm(enc_bf16, n * m->S, m->D, m->cross_wkv, m->L * 2 * m->D, m->cross_bkv, EPI_STORE_BF16,
+                            c->cross_kv + (size_t)cache_off * m->S * m->D, m->D);
+    g.n_seg_ptrs = 0;
+    g.seg_cols = m->D;
+    g.seg_stride = (int64_t)c->B * m->S * m->D;
+    return gemm_run(m->stream, g, m->gemm_impl);
+}
+
+// Encode n <= enc_batch chunks.  Outputs (any may be null): fp32 enc_out, cross K/V into `into`.
+static int encode_batch(Model *m, const float *mel_dev, int n, float *enc_out_dev, Cache *into, int cache_off) {
+    WB_CHECK(ensure_encoder_ws(m, n));
+    cudaStream_t st = m->stream;
+    const int D = m->D, S = m->S, NF = m->n_frames, M = n * S, impl = m->gemm_impl;
+    const float *W = m->w32;
+    WB_CHECK(mel_to_bf16_T(st, mel_dev, m->e_melT, n, m->NM, NF));
+    {  // conv1 + GELU (whisper.mojo:73-75) as a 3-tap implicit GEMM over [frames][128 padded channels]
+        GemmDesc g;
+        g.A = m->e_melT, g.a_batch_stride = (int64_t)NF * 128, g.lda = 128, g.src_rows = NF;
+        g.conv_stride = 1, g.pad = 1, g.taps = 3, g.Cin = 128, g.batches = n, g.rows_per_batch = NF;
+        g.W = m->conv1_w, g.N = D, g.bias = W + m->lay.conv1_b, g.epi = EPI_GELU_BF16;
+        g.out[0] = m->e_x1T, g.out_ld[0] = D;
+        WB_CHECK(gemm_run(st, g, impl));
+    }
+    {  // conv2 (stride 2) + GELU + positional embedding (whisper.mojo:78-89)
+        GemmDesc g;
+        g.A = m->e_x1T, g.a_batch_stride = (int64_t)NF * D, g.lda = D, g.src_rows = NF;
+        g.conv_stride = 2, g.pad = 1, g.taps = 3, g.Cin = D, g.batches = n, g.rows_per_batch = S;
+        g.W = m->conv2_w, g.N = D, g.bias = W + m->lay.conv2_b, g.epi = EPI_GELU_POS_F32;
+        g.out[0] = m->e_x, g.out_ld[0] = D, g.pos = W + m->lay.enc_pos;
+        WB_CHECK(gemm_run(st, g, impl));
+    }
+    for (int l = 0; l < m->L; l++) {  // layers.mojo:435-519 with is_decoder = False
+        const LayerDev &d = m->enc[l];
+        WB_CHECK(ln_bf16(st, m->e_x, d.ln1_g, d.ln1_b, M, D, m->e_xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, m->e_qkv, 3 * D), impl));
+        WB_CHECK(encoder_attention_ref(st, m->e_qkv, m->e_attn, n, S, m->H, D));
+        WB_CHECK(gemm_run(st, plain_gemm(m->e_attn, M, D, d.wo, D, d.bo, EPI_RESID_F32, m->e_x, D), impl));
+        WB_CHECK(ln_bf16(st, m->e_x, d.ln3_g, d.ln3_b, M, D, m->e_xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.w1, m->F, d.b1, EPI_GELU_BF16, m->e_h, m->F), impl));
+        WB_CHECK(gemm_run(st, plain_gemm(m->e_h, M, m->F, d.w2, D, d.b2, EPI_RESID_F32, m->e_x, D), impl));
+    }
+    WB_CHECK(ln_bf16(st, m->e_x, W + m->lay.enc_ln_w, W + m->lay.enc_ln_b, M, D, m->e_enc, enc_out_dev));
+    if (into) WB_CHECK(cross_kv_project(m, m->e_enc, n, into, cache_off));
+    return WB_OK;
+}
+
+int model_encode(Model *m, const float *mel_dev, int n, float *enc_out_dev, Cache *into, int cache_off) {
+    WB_ARG(m->loaded, "encode before weights are loaded");
+    const size_t mel_per = (size_t)m->NM * m->n_frames, enc_per = (size_t)m->S * m->D;
+    for (int i = 0; i < n; i += m->enc_batch) {
+        int nb = std::min(m->enc_batch, n - i);
+        WB_CHECK(encode_batch(m, mel_dev + i * mel_per, nb, enc_out_dev ? enc_out_dev + i * enc_per : nullptr, into,
+                              cache_off + i));
+    }
+    if (into) into->has_cross = true;
+    return WB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KV cache (layers.mojo:14-69) and decode workspace
+// ---------------------------------------------------------------------------------------------
+int cache_create(Model *m, int B, int max_len, bool want_logits, Cache **out) {
+    WB_ARG(B > 0 && max_len > 0 && max_len <= m->T, "kvcache: bad size (B=%d max_len=%d n_text_ctx=%d)", B, max_len,
+           m->T);
+    Cache *c = new Cache();
+    c->m = m, c->B = B, c->T = max_len;
+    const size_t D = m->D;
+    auto A = [&](auto **p, size_t n) {
+        void *q = nullptr;
+        if (cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(**p)) != cudaSuccess) {
+            set_error("kvcache: cudaMalloc of %zu bytes failed", n * sizeof(**p));
+            return false;
+        }
+        *p = static_cast<std::remove_reference_t<decltype(*p)>>(q);
+        return true;
+    };
+    const int tiles_n = gemm_tiles_n(m->V);
+    c->cross_splits = decode_attention_splits(B, m->S);
+    bool ok = A(&c->self_kv, (size_t)m->L * 2 * B * max_len * D) && A(&c->cross_kv, (size_t)m->L * 2 * B * m->S * D) &&
+              A(&c->x, B * D) && A(&c->xn, B * D) && A(&c->q, B * D) && A(&c->attn, B * D) &&
+              A(&c->h, (size_t)B * m->F) && A(&c->part_val, (size_t)B * tiles_n) &&
+              A(&c->part_idx, (size_t)B * tiles_n) && A(&c->next, B) &&
+              A(&c->attn_ws, (size_t)B * c->cross_splits * m->H * 66) &&
+              A(&c->g.tokens_out, (size_t)B * (5 + m->cfg.max_iters)) && A(&c->g.out_len, B) && A(&c->g.cur_tok, B) &&
+              A(&c->g.done, B) && A(&c->g.scalars, 4);
+    if (ok && (want_logits || m->gemm_impl == GEMM_IMPL_REF)) ok = A(&c->logits, (size_t)B * m->V);
+    if (ok && cudaMallocHost((void **)&c->pinned_scalars, 4 * sizeof(int)) != cudaSuccess) ok = false;
+    if (!ok) {
+        cache_destroy(c);
+        return WB_ERR_CUDA;
+    }
+    c->g.T_out = 5 + m->cfg.max_iters, c->g.eot = m->cfg.eot, c->g.pos_quirk = m->cfg.pos_quirk;
+    *out = c;
+    return cache_reset(c);
+}
+
+void cache_destroy(Cache *c) {
+    if (!c) return;
+    if (c->m) cudaStreamSynchronize(c->m->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    void *ptrs[] = {c->self_kv, c->cross_kv, c->x, c->xn, c->q, c->attn, c->h, c->part_val, c->part_idx, c->next,
+                    c->attn_ws, c->logits, c->g.tokens_out, c->g.out_len, c->g.cur_tok, c->g.done, c->g.scalars};
+    for (void *p : ptrs) cudaFree(p);
+    if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
+    delete c;
+}
+
+int cache_reset(Cache *c) {
+    Model *m = c->m;
+    // the reference zero-fills its cache tensors (layers.mojo:30-36)
+    WB_CUDA(cudaMemsetAsync(c->self_kv, 0, (size_t)m->L * 2 * c->B * c->T * m->D * sizeof(bf16), m->stream));
+    WB_CHECK(greedy_init(m->stream, c->g, c->B, m->cfg.prompt));
+    c->host_len = 0;
+    c->has_cross = false;
+    return WB_OK;
+}
+
+int cache_set_encoder(Cache *c, const float *enc_out_dev) {
+    Model *m = c->m;
+    WB_ARG(m->loaded, "kvcache_set_encoder before weights are loaded");
+    const size_t per = (size_t)m->S * m->D;
+    for (int i = 0; i < c->B; i += m->enc_batch) {
+        int nb = std::min(m->enc_batch, c->B - i);
+        WB_CHECK(ensure_encoder_ws(m, nb));
+        WB_CHECK(convert_f32_bf16(m->stream, enc_out_dev + i * per, m->e_enc, nb * per));
+        WB_CHECK(cross_kv_project(m, m->e_enc, nb, c, i));
+    }
+    c->has_cross = true;
+    return WB_OK;
+}
+
+static int timed_cross_attention(Model *m, const DecodeAttnArgs &a) {
+    if (!m->profile_attn) return decode_attention(m->stream, a);
+    KernelTimer &t = m->cross_timer;
+    while ((int)t.ev.size() < t.used + 2) {
+        cudaEvent_t e;
+        WB_CUDA(cudaEventCreate(&e));
+        t.ev.push_back(e);
+    }
+    WB_CUDA(cudaEventRecord(t.ev[t.used], m->stream));
+    int rc = decode_attention(m->stream, a);
+    WB_CUDA(cudaEventRecord(t.ev[t.used + 1], m->stream));
+    t.used += 2;
+    return rc;
+}
+
+// One decoder forward with q_len = 1 for every chunk of the cache (whisper.mojo:130-167,
+// layers.mojo:435-519 with is_decoder = True).  Token / position / cur_len come from device memory.
+int decode_step(Cache *c, bool with_logits, bool store_logits) {
+    Model *m = c->m;
+    cudaStream_t st = m->stream;
+    const int B = c->B, D = m->D, impl = m->gemm_impl;
+    const float *W = m->w32;
+    int *cur_len = c->g.scalars, *pos = c->g.scalars + 1;
+    const size_t self_seg = (size_t)B * c->T * D, cross_seg = (size_t)B * m->S * D;
+    WB_CHECK(embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, c->g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
+                      m->dec[0].ln1_b, c->x, c->xn));
+    for (int l = 0; l < m->L; l++) {
+        const LayerDev &d = m->dec[l];
+        bf16 *sk = c->self_kv + (size_t)(l * 2) * self_seg, *sv = sk + self_seg;
+        bf16 *ck = c->cross_kv + (size_t)(l * 2) * cross_seg, *cv = ck + cross_seg;
+        if (l > 0) WB_CHECK(ln_bf16(st, c->x, d.ln1_g, d.ln1_b, B, D, c->xn, nullptr));
+        {  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
+            GemmDesc g = plain_gemm(c->xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, c->q, D);
+            g.n_seg_ptrs = 3, g.seg_cols = D;
+            g.out[1] = sk, g.out_ld[1] = (int64_t)c->T * D, g.dyn_mult[1] = D;
+            g.out[2] = sv, g.out_ld[2] = (int64_t)c->T * D, g.dyn_mult[2] = D;
+            g.dyn_off = cur_len;
+            WB_CHECK(gemm_run(st, g, impl));
+        }
+        DecodeAttnArgs a;
+        a.q = c->q, a.K = sk, a.V = sv, a.out = c->attn, a.kv_batch_stride = (int64_t)c->T * D;
+        a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
+        a.splits = 1, a.ws = nullptr;
+        WB_CHECK(decode_attention(st, a));
+        WB_CHECK(gemm_run(st, plain_gemm(c->attn, B, D, d.wo, D, d.bo, EPI_RESID_F32, c->x, D), impl));
+        // cross attention over the encoder positions (layers.mojo:463-488)
+        WB_CHECK(ln_bf16(st, c->x, d.ln2_g, d.ln2_b, B, D, c->xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(c->xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, c->q, D), impl));
+        a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;
+        a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
+        a.splits = c->cross_splits, a.ws = c->attn_ws;
+        WB_CHECK(timed_cross_attention(m, a));
+        WB_CHECK(gemm_run(st, plain_gemm(c->attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, c->x, D), impl));
+        // MLP (layers.mojo:490-517)
+        WB_CHECK(ln_bf16(st, c->x, d.ln3_g, d.ln3_b, B, D, c->xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(c->xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, c->h, m->F), impl));
+        WB_CHECK(gemm_run(st, plain_gemm(c->h, B, m->F, d.w2, D, d.b2, EPI_RESID_F32, c->x, D), impl));
+    }
+    if (with_logits) {  // whisper.mojo:156-166 + argmax :198,219
+        WB_CHECK(ln_bf16(st, c->x, W + m->lay.dec_ln_w, W + m->lay.dec_ln_b, B, D, c->xn, nullptr));
+        GemmDesc g = plain_gemm(c->xn, B, D, m->tok_emb_bf16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
+        g.part_val = c->part_val, g.part_idx = c->part_idx;
+        g.logits = (store_logits || impl == GEMM_IMPL_REF) ? c->logits : nullptr;
+        WB_ARG(!(store_logits || impl == GEMM_IMPL_REF) || c->logits, "decode_step: cache has no logits buffer");
+        WB_CHECK(gemm_run(st, g, impl));
+        WB_CHECK(argmax_partials(st, c->part_val, c->part_idx, B, gemm_tiles_n(m->V), c->next));
+    }
+    return WB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whisper.transcribe (whisper.mojo:184-223), batched
+// ---------------------------------------------------------------------------------------------
+static int greedy_loop(Cache *c) {
+    Model *m = c->m;
+    cudaStream_t st = m->stream;
+    const int B = c->B;
+    // prefill: the reference runs the 4 prompt ids as one q_len = 4 forward with a causal mask
+    // (whisper.mojo:195-197); feeding them one by one through the cached step computes the same
+    // thing (masked scores are exp(-1e10 - max) = 0 there) and only the last position's logits are used.
+    for (int i = 0; i < 4; i++) {
+        WB_CHECK(decode_step(c, i == 3, false));
+        if (i < 3) WB_CHECK(greedy_advance(st, c->g, B, 0, m->cfg.prompt[i + 1], nullptr));
+        else WB_CHECK(greedy_advance(st, c->g, B, 1, 0, c->next));
+    }
+    const bool graph = m->use_graph && !m->profile_attn;
+    if (graph && !c->graph_exec) {
+        cudaGraph_t gr = nullptr;
+        WB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_step(c, true, false);
+        if (rc == WB_OK) rc = greedy_advance(st, c->g, B, 1, 0, c->next);
+        cudaError_t e = cudaStreamEndCapture(st, &gr);
+        if (rc != WB_OK) {
+            if (gr) cudaGraphDestroy(gr);
+            return rc;
+        }
+        WB_CUDA(e);
+        WB_CUDA(cudaGraphInstantiate(&c->graph_exec, gr, 0));
+        cudaGraphDestroy(gr);
+    }
+    for (int it = 0; it < m->cfg.max_iters; it++) {  // whisper.mojo:205
+        if ((it & 15) == 0) {                         // `if next_token == 50257: break`, polled every 16 steps
+            WB_CUDA(cudaMemcpyAsync(c->pinned_scalars, c->g.scalars, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            WB_CUDA(cudaStreamSynchronize(st));
+            if (c->pinned_scalars[2] >= B) break;
+        }
+        if (graph) {
+            WB_CUDA(cudaGraphLaunch(c->graph_exec, st));
+            g_launches.fetch_add(12 * m->L + 4, std::memory_order_relaxed);  // kernels replayed by the graph
+        } else {
+            WB_CHECK(decode_step(c, true, false));
+            WB_CHECK(greedy_advance(st, c->g, B, 1, 0, c->next));
+        }
+    }
+    return WB_OK;
+}
+
+int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
+                     int32_t *out_len_dev) {
+    WB_ARG(m->loaded, "transcribe before weights are loaded");
+    WB_ARG(n > 0 && (mel_dev || pcm_dev) && out_tokens_dev && out_len_dev, "transcribe: bad arguments");
+    cudaStream_t st = m->stream;
+    const int T_out = 5 + m->cfg.max_iters;
+    const int T_cache = std::min(m->T, (T_out + 7) & ~7);
+    cudaEvent_t ev[5];
+    for (auto &e : ev) WB_CUDA(cudaEventCreate(&e));
+    float acc[4] = {0, 0, 0, 0};
+    m->cross_timer.used = 0;
+    const size_t mel_per = (size_t)m->NM * m->n_frames;
+    int wave = std::min(n, m->wave_max);
+    {  // bound the cross K/V cache to about half of the free HBM
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        size_t per_chunk = (size_t)m->L * 2 * (m->S + T_cache) * m->D * sizeof(bf16);
+        size_t cap = std::max<size_t>(1, (free_b / 2) / per_chunk);
+        wave = (int)std::min<size_t>(wave, cap);
+    }
+    Cache *c = nullptr;
+    float *mel_tmp = nullptr;
+    int rc = WB_OK;
+    for (int w0 = 0; w0 < n && rc == WB_OK; w0 += wave) {
+        const int nb = std::min(wave, n - w0);
+        if (!c || c->B != nb) {
+            if (c) cache_destroy(c);
+            c = nullptr;
+            rc = cache_create(m, nb, T_cache, false, &c);
+            if (rc != WB_OK) break;
+        } else {
+            rc = cache_reset(c);
+            if (rc != WB_OK) break;
+        }
+        cudaEventRecord(ev[0], st);
+        const float *mel_w = mel_dev ? mel_dev + w0 * mel_per : nullptr;
+        if (!mel_dev) {  // frontend
+            if (!mel_tmp && cudaMalloc((void **)&mel_tmp, (size_t)wave * mel_per * 4) != cudaSuccess) {
+                set_error("transcribe: cannot allocate the log-mel buffer");
+                rc = WB_ERR_CUDA;
+                break;
+            }
+            rc = model_logmel(m, pcm_dev + (size_t)w0 * m->n_samples, nb, mel_tmp);
+            if (rc != WB_OK) break;
+            mel_w = mel_tmp;
+        }
+        cudaEventRecord(ev[1], st);
+        rc = model_encode(m, mel_w, nb, nullptr, c, 0);
+        if (rc != WB_OK) break;
+        cudaEventRecord(ev[2], st);
+        rc = greedy_loop(c);
+        if (rc != WB_OK) break;
+        cudaEventRecord(ev[3], st);
+        cudaMemcpyAsync(out_tokens_dev + (size_t)w0 * T_out, c->g.tokens_out, (size_t)nb * T_out * 4,
+                        cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(out_len_dev + w0, c->g.out_len, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("transcribe: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = WB_ERR_CUDA;
+            break;
+        }
+        float ms;
+        for (int i = 0; i < 3; i++) {
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            acc[i == 0 ? 0 : (i == 1 ? 1 : 3)] += ms;
+        }
+    }
+    if (rc == WB_OK) {
+        // cross-K/V projection time is part of encode_batch; report it inside [1] and leave [2] = 0
+        m->timing[0] = acc[0], m->timing[1] = acc[1], m->timing[2] = 0.f, m->timing[3] = acc[3];
+        m->timing[4] = acc[0] + acc[1] + acc[3];
+        KernelTimer &t = m->cross_timer;
+        t.total_ms = 0.f, t.launches = 0;
+        for (int i = 0; i + 1 < t.used; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.total_ms += ms, t.launches++;
+        }
+    }
+    if (c) cache_destroy(c);
+    if (mel_tmp) cudaFree(mel_tmp);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// step-wise API and teacher forcing (tests / WhisperDecoder.forward mirror)
+// ---------------------------------------------------------------------------------------------
+static int set_step_state(Cache *c, int cur_len, int pos, const int32_t *tokens_host) {
+    Model *m = c->m;
+    int sc[2] = {cur_len, pos};
+    WB_CUDA(cudaMemcpyAsync(c->g.scalars, sc, sizeof sc, cudaMemcpyHostToDevice, m->stream));
+    WB_CUDA(cudaMemcpyAsync(c->g.cur_tok, tokens_host, (size_t)c->B * 4, cudaMemcpyHostToDevice, m->stream));
+    WB_CUDA(cudaStreamSynchronize(m->stream));  // sc is a stack variable
+    return WB_OK;
+}
+
+int cache_step_api(Cache *c, const int32_t *tokens_host, int start_pos, float *logits_host, int32_t *next_host) {
+    Model *m = c->m;
+    WB_ARG(m->loaded && c->has_cross, "decode_step: weights / encoder output not set");
+    WB_ARG(tokens_host, "decode_step: null tokens");
+    WB_ARG(c->host_len < c->T, "decode_step: cache full (%d)", c->T);
+    WB_ARG(start_pos >= 0 && start_pos < m->T, "decode_step: start_pos %d out of range", start_pos);
+    WB_ARG(!logits_host || c->logits, "decode_step: cache was created without a logits buffer");
+    WB_CHECK(set_step_state(c, c->host_len, start_pos, tokens_host));
+    WB_CHECK(decode_step(c, true, logits_host != nullptr));
+    c->host_len++;
+    if (logits_host)
+        WB_CUDA(cudaMemcpyAsync(logits_host, c->logits, (size_t)c->B * m->V * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (next_host) WB_CUDA(cudaMemcpyAsync(next_host, c->next, (size_t)c->B * 4, cudaMemcpyDeviceToHost, m->stream));
+    WB_CUDA(cudaStreamSynchronize(m->stream));
+    return WB_OK;
+}
+
+int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_t *forced_host, int n_forced,
+                         float *logits_host) {
+    WB_ARG(m->loaded, "teacher_forced before weights are loaded");
+    WB_ARG(n > 0 && n_forced >= 4 && n_forced <= m->T && enc_out_dev && forced_host && logits_host,
+           "teacher_forced: bad arguments");
+    Cache *c = nullptr;
+    WB_CHECK(cache_create(m, n, std::min(m->T, (n_forced + 7) & ~7), true, &c));
+    int rc = cache_set_encoder(c, enc_out_dev);
+    std::vector<int32_t> col(n);
+    for (int i = 0; i < n_forced && rc == WB_OK; i++) {
+        for (int b = 0; b < n; b++) col[b] = forced_host[(size_t)b * n_forced + i];
+        const int pos = i < 4 ? i : i - m->cfg.pos_quirk;  // whisper.mojo:196,217
+        rc = set_step_state(c, i, pos, col.data());
+        if (rc == WB_OK) rc = decode_step(c, i >= 3, i >= 3);
+        if (rc == WB_OK && i >= 3) {
+            // logits_host is [n][n_forced-3][V]; this step is row i-3 of every chunk
+            cudaError_t e = cudaMemcpy2DAsync(logits_host + (size_t)(i - 3) * m->V,
+                                              (size_t)(n_forced - 3) * m->V * 4, c->logits, (size_t)m->V * 4,
+                                              (size_t)m->V * 4, n, cudaMemcpyDeviceToHost, m->stream);
+            if (e != cudaSuccess || cudaStreamSynchronize(m->stream) != cudaSuccess) {
+                set_error("teacher_forced: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = WB_ERR_CUDA;
+            }
+        }
+    }
+    cache_destroy(c);
+    return rc;
+}
+
+}  // namespace wb

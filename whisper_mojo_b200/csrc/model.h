@@ -1,0 +1,106 @@
+// model.h -- model-level state of the batched fast path (model.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/whisper_b200.h"
+#include "kernels.h"
+
+namespace wb {
+
+typedef __nv_bfloat16 bf16;
+
+struct AttnW {  // offsets (in floats) into the fp32 weight image; layers.mojo:96-103
+    int64_t q_w, q_b, k_w, v_w, v_b, o_w, o_b;
+};
+struct BlockW {  // layers.mojo:418-433
+    AttnW attn;
+    int64_t attn_ln_w, attn_ln_b;
+    AttnW cross;
+    int64_t cross_ln_w, cross_ln_b;
+    int64_t fc1_w, fc1_b, fc2_w, fc2_b, mlp_ln_w, mlp_ln_b;
+};
+struct Layout {  // export_weights.py:19-90
+    int64_t conv1_w, conv1_b, conv2_w, conv2_b, enc_pos;
+    std::vector<BlockW> enc, dec;
+    int64_t enc_ln_w, enc_ln_b, tok_emb, dec_pos, dec_ln_w, dec_ln_b;
+    int64_t total;
+    std::vector<std::pair<int64_t, int64_t>> tensors;  // (offset, count) in file order
+};
+Layout make_layout(const wm_config &c);
+
+struct LayerDev {
+    bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    bf16 *cwq = nullptr, *cwo = nullptr;  // decoder cross-attention
+    float *bqkv = nullptr;                // [3D]: q bias, zeros (k has no bias), v bias
+    const float *bo, *b1, *b2, *cbq, *cbo;
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;  // attn_ln, cross_ln (dec), mlp_ln
+};
+
+struct KernelTimer {
+    std::vector<cudaEvent_t> ev;
+    int used = 0;
+    float total_ms = 0.f;
+    int64_t launches = 0;
+};
+
+struct Model {
+    wm_config cfg;
+    int D, H, L, V, S, T, NM, F, n_frames, n_samples;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int gemm_impl = 1, attn_impl = 0, use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048;
+    Layout lay;
+    float *w32 = nullptr;
+    bool loaded = false;
+    bf16 *conv1_w = nullptr, *conv2_w = nullptr, *tok_emb_bf16 = nullptr, *cross_wkv = nullptr;
+    float *cross_bkv = nullptr;
+    std::vector<LayerDev> enc, dec;
+    FrontendTables ft;
+    std::vector<void *> owned;
+    // encoder workspace (sized for enc_cap chunks)
+    int enc_cap = 0;
+    bf16 *e_melT = nullptr, *e_x1T = nullptr, *e_xn = nullptr, *e_qkv = nullptr, *e_attn = nullptr, *e_h = nullptr,
+         *e_enc = nullptr;
+    float *e_x = nullptr;
+    float timing[5] = {0, 0, 0, 0, 0};
+    KernelTimer cross_timer;
+};
+
+struct Cache {
+    Model *m = nullptr;
+    int B = 0, T = 0;
+    int host_len = 0;  // mirror of current_len for the step-wise API
+    bool has_cross = false;
+    bf16 *self_kv = nullptr;   // [L][2][B][T][D]
+    bf16 *cross_kv = nullptr;  // [L][2][B][S][D]
+    // decode workspace
+    float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr;
+    bf16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr;
+    int *part_idx = nullptr, *next = nullptr;
+    int cross_splits = 1;
+    GreedyState g;
+    int *pinned_scalars = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+};
+
+int model_create(const wm_config *cfg, void *stream, Model **out);
+void model_destroy(Model *m);
+int model_load(Model *m, const float *host, int64_t n_floats);
+int model_logmel(Model *m, const float *pcm_dev, int n, float *mel_dev);
+int model_encode(Model *m, const float *mel_dev, int n, float *enc_out_dev, Cache *into, int cache_off);
+int cache_create(Model *m, int B, int max_len, bool want_logits, Cache **out);
+void cache_destroy(Cache *c);
+int cache_reset(Cache *c);
+int cache_set_encoder(Cache *c, const float *enc_out_dev);
+int decode_step(Cache *c, bool with_logits, bool store_logits);
+int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
+                     int32_t *out_len_dev);
+int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_t *forced_host, int n_forced,
+                         float *logits_host);
+int cache_step_api(Cache *c, const int32_t *tokens_host, int start_pos, float *logits_host, int32_t *next_host);
+
+}  // namespace wb

@@ -1,0 +1,100 @@
+"""GPU: the fast path's kernels in isolation -- tcgen05/TMA GEMM (all epilogues, conv taps) against
+the CUDA-core kernel and fp64 numpy on bf16-rounded operands; decode attention; log-mel frontend."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from gpu_util import bf16_round, debug_decode_attention, debug_gemm
+from oracle import logmel_oracle as LM
+from whisper_mojo_b200 import Whisper, WhisperConfig, synth
+
+pytestmark = pytest.mark.gpu
+rng = np.random.default_rng(1)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1, 1000, 128), (4, 3241, 384), (200, 1152, 384), (300, 384, 1536), (129, 130, 192)])
+def test_gemm_tc_all_epilogues(M, N, K):
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+    b = rng.standard_normal(N, dtype=np.float32)
+    ref = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T + b
+    tol = 2e-5 * max(1.0, K / 64)
+    for impl in (0, 1):
+        assert np.abs(debug_gemm(impl, A, W, b, 3) - ref).max() <= tol  # fp32 store: bit-level bf16 x bf16 products
+    assert np.array_equal(debug_gemm(1, A, W, b, 0), bf16_round(debug_gemm(1, A, W, b, 3)))  # bf16 store = rounded fp32
+    g = torch.nn.functional.gelu(torch.from_numpy(ref), approximate="tanh").numpy()
+    assert np.abs(debug_gemm(1, A, W, b, 1) - g).max() <= 2e-2  # bf16 output, |g| <~ 5
+    x0 = rng.standard_normal((M, N), dtype=np.float32)
+    assert np.abs(debug_gemm(1, A, W, b, 2, out0=x0) - (x0 + ref)).max() <= tol
+    lg = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
+    for impl in (0, 1):
+        am = debug_gemm(impl, A, W, None, 4)
+        assert np.array_equal(am[:, -1].astype(np.int64), lg.argmax(1))
+        assert np.abs(am[:, :-1] - lg[:, :-1]).max() <= tol
+
+
+def test_gemm_argmax_ties_pick_lowest_index():
+    A = np.zeros((3, 64), np.float32)
+    A[:, 0] = 1.0
+    W = np.zeros((700, 64), np.float32)
+    W[[5, 300, 650], 0] = 2.0  # equal maxima in three different 128-column tiles
+    W[[130, 131], 0] = 2.0
+    am = debug_gemm(1, A, W, None, 4)
+    assert np.all(am[:, -1] == 5)
+
+
+@pytest.mark.parametrize("cs,Cin,L,N,B", [(1, 128, 300, 128, 2), (2, 128, 301, 256, 3), (2, 384, 3000, 384, 2), (1, 128, 3000, 384, 1)])
+def test_gemm_conv_taps(cs, Cin, L, N, B):
+    A = rng.standard_normal((B, L, Cin), dtype=np.float32)
+    W = rng.standard_normal((N, 3 * Cin), dtype=np.float32) / np.sqrt(3 * Cin)
+    Lo = (L + 2 - 3) // cs + 1
+    Ab, Wb = bf16_round(A).astype(np.float64), bf16_round(W).astype(np.float64)
+    ref = np.zeros((B, Lo, N))
+    for t in range(3):
+        rows = np.arange(Lo) * cs + t - 1
+        ok = (rows >= 0) & (rows < L)
+        ref[:, ok] += Ab[:, rows[ok]] @ Wb[:, t * Cin:(t + 1) * Cin].T  # zero padding outside the chunk
+    for impl in (0, 1):
+        out = debug_gemm(impl, A, W, None, 3, batches=B, taps=3, conv_stride=cs, pad=1, rows_per_batch=Lo)
+        assert np.abs(out.reshape(B, Lo, N) - ref).max() <= 1e-4, impl
+
+
+@pytest.mark.parametrize("B,H,ln,splits", [(3, 6, 1500, 1), (3, 6, 1500, 11), (2, 2, 96, 1), (2, 12, 200, 1), (1, 6, 1, 1),
+                                           (2, 6, 2, 1), (2, 6, 3, 1), (2, 6, 17, 1), (2, 6, 19, 1), (1, 6, 1500, 7)])
+def test_decode_attention(B, H, ln, splits):
+    D = H * 64
+    q = bf16_round(rng.standard_normal((B, D), dtype=np.float32) * 1.5)
+    K = bf16_round(rng.standard_normal((B, ln, D), dtype=np.float32) * 1.5)
+    V = bf16_round(rng.standard_normal((B, ln, D), dtype=np.float32))
+    out = debug_decode_attention(q, K, V, H, splits)
+    qh, Kh, Vh = (x.astype(np.float64) for x in (q.reshape(B, H, 64), K.reshape(B, ln, H, 64), V.reshape(B, ln, H, 64)))
+    s = np.einsum("bhd,bjhd->bhj", qh, Kh) * 0.125
+    p = np.exp(s - s.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    ref = np.einsum("bhj,bjhd->bhd", p, Vh).reshape(B, D)
+    assert np.abs(out - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max() / 2)  # bf16 output rounding
+
+
+def test_logmel_frontend_matches_hf_golden_and_oracle():
+    m = Whisper(WhisperConfig.tiny())
+    g = np.load(os.path.join(GOLDEN, "logmel_hf.npz"))
+    a = synth.make_audio(int(g["n_chunks"]), seed=int(g["seed"]))
+    mel = m.log_mel(a)
+    rngv = float(g["mel_max"].max() - g["mel_min"].min())
+    # tolerance: north_star "log-mel within 1e-4 relative"; formula max|a-b| / (max(b) - min(b))
+    assert np.abs(mel[:, :, :64] - g["mel_first_frames"]).max() / rngv <= 1e-4
+    assert np.abs(mel[:, :, -64:] - g["mel_last_frames"]).max() / rngv <= 1e-4
+    assert np.abs(mel.astype(np.float64).sum(axis=2) - g["mel_row_sums"]).max() / 3000 <= 1e-5
+    ref = LM.log_mel(a)
+    assert np.abs(mel - ref).max() / (ref.max() - ref.min()) <= 1e-4
+    # edge cases: silence (everything at the 1e-10 floor), a full-scale click, 5 s audio zero padded
+    edge = np.zeros((3, 480000), np.float32)
+    edge[1, 1234] = 1.0
+    edge[2, :80000] = np.random.default_rng(3).standard_normal(80000).astype(np.float32)
+    me, re_ = m.log_mel(edge), LM.log_mel(edge)
+    assert np.abs(me - re_).max() / max(re_.max() - re_.min(), 1.0) <= 1e-4
+    assert np.all(me[0] == me[0, 0, 0]) and abs(me[0, 0, 0] - (-10 + 4) / 4) < 1e-6
+    assert np.abs(me[2, :, :64] - g["short_first_frames"]).max() <= 1e-4

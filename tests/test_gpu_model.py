@@ -1,0 +1,226 @@
+"""GPU: model-level parity of the batched fast path against the CPU oracle on seeded inputs, plus
+the op-by-op engine, batch invariance, the step API and error behaviour.
+
+Tolerances (written here, justified in DESIGN.md "Precision"): the fast path stores weights, GEMM
+operands and the KV cache in bf16 with fp32 accumulation and an fp32 residual stream.  On these
+synthetic weights the fp32 oracle itself moves by 2.1e-2 (enc_out) / 4e-2 (logits) when only the
+weights are rounded to bf16, so the bounds below are: enc_out max-abs <= 4e-2 (mean-abs <= 6e-3),
+logits max-abs <= 1e-1 (median <= 1e-2), greedy ids identical to the oracle up to the first step whose
+fp32 top-1/top-2 margin is below 0.1.  The op-by-op engine is fp32 and is held to 1e-4 / exact ids.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import tokens_agree_up_to_margin
+from oracle import oracle as O
+from whisper_mojo_b200 import DeviceKVCache, Tensor, WeightLoader, Whisper, WhisperConfig, _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+ENC_MAX, ENC_MEAN, LOGIT_MAX, LOGIT_MEDIAN, MARGIN_TAU = 4e-2, 6e-3, 1e-1, 1e-2, 0.1
+
+
+def build(cfg, engine="fast", seed=0, **opts):
+    w = synth.make_weights(cfg, seed=seed)
+    m = Whisper(cfg, engine=engine)
+    for k, v in opts.items():
+        m.set_option(k, v)
+    m.load(WeightLoader(data=w))
+    return m, w
+
+
+@pytest.fixture(scope="module", params=["micro", "tiny"])
+def setup(request):
+    cfg = WhisperConfig.micro() if request.param == "micro" else WhisperConfig.tiny()
+    n = 3
+    mel = synth.make_mel(n, cfg, 0)
+    m, w = build(cfg)
+    om = O.OracleWhisper(cfg, w)
+    enc_ref = np.stack([om.encode(mel[i]) for i in range(n)])
+    return cfg, mel, m, om, enc_ref
+
+
+def test_encoder_matches_oracle(setup):
+    cfg, mel, m, om, enc_ref = setup
+    enc = m.encode(mel)
+    err = np.abs(enc - enc_ref)
+    assert err.max() <= ENC_MAX and err.mean() <= ENC_MEAN, (err.max(), err.mean())
+    assert np.array_equal(m.encode(mel[1:2])[0], enc[1])  # independent of batch size / position
+
+
+def test_teacher_forced_logits_match_oracle(setup):
+    cfg, mel, m, om, enc_ref = setup
+    n = len(mel)
+    forced = np.stack([np.concatenate([np.array(cfg.prompt), np.random.default_rng(10 + i).integers(0, cfg.vocab_size, 12)])
+                       for i in range(n)]).astype(np.int32)
+    ref = np.stack([om.teacher_forced(enc_ref[i], forced[i]) for i in range(n)])
+    lg = m.teacher_forced(torch.from_numpy(enc_ref).cuda(), forced)
+    err = np.abs(lg - ref)
+    assert err.max() <= LOGIT_MAX and np.median(err) <= LOGIT_MEDIAN, (err.max(), np.median(err))
+    top2 = np.sort(ref, axis=-1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > MARGIN_TAU
+    assert np.array_equal(lg.argmax(-1)[clear], ref.argmax(-1)[clear])
+
+
+def test_greedy_tokens_match_oracle(setup):
+    cfg, mel, m, om, enc_ref = setup
+    toks, lens = m.transcribe_batch(mel)
+    assert toks.shape == (len(mel), cfg.max_tokens)
+    for i in range(len(mel)):
+        ref, mg = om.greedy(enc_ref[i], margins=True)
+        got = toks[i, :lens[i]]
+        assert list(got[:4]) == list(cfg.prompt)
+        ok, msg = tokens_agree_up_to_margin(got, ref, mg, MARGIN_TAU)
+        assert ok, f"chunk {i}: {msg}"
+        assert np.all(toks[i, lens[i]:] == -1)
+    # main.mojo's call: one mel in, list of ids out
+    one = m.transcribe(mel[0])
+    assert one == [int(t) for t in toks[0, :lens[0]]]
+    # a chunk's ids do not depend on batch size or position in the batch
+    t2, l2 = m.transcribe_batch(mel[::-1].copy())
+    assert np.array_equal(t2[::-1], toks) and np.array_equal(l2[::-1], lens)
+
+
+def test_reference_kernels_agree_with_tensor_core_kernels(setup):
+    cfg, mel, m, om, enc_ref = setup
+    m0, _ = build(cfg, gemm_impl=0)
+    e0, e1 = m0.encode(mel[:1]), m.encode(mel[:1])
+    assert np.abs(e0 - e1).max() <= 2e-2  # same bf16 rounding points, different summation order
+    t0, l0 = m0.transcribe_batch(mel[:1])
+    t1, l1 = m.transcribe_batch(mel[:1])
+    ref, mg = om.greedy(enc_ref[0], margins=True)
+    assert tokens_agree_up_to_margin(t0[0, :l0[0]], ref, mg, MARGIN_TAU)[0]
+    assert tokens_agree_up_to_margin(t1[0, :l1[0]], ref, mg, MARGIN_TAU)[0]
+
+
+def test_graph_and_eager_decode_are_identical(setup):
+    cfg, mel, m, om, enc_ref = setup
+    t1, l1 = m.transcribe_batch(mel)
+    m.set_option("use_graph", 0)
+    t0, l0 = m.transcribe_batch(mel)
+    m.set_option("use_graph", 1)
+    assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
+
+
+def test_step_api_matches_transcribe(setup):
+    """WhisperDecoder.forward([tok], enc_out, cache, True, start_pos) driven from the host reproduces
+    the device-side greedy loop, including the reference's start_pos = current_len - 1."""
+    cfg, mel, m, om, enc_ref = setup
+    toks, lens = m.transcribe_batch(mel[:2])
+    enc = torch.from_numpy(m.encode(mel[:2])).cuda()
+    cache = DeviceKVCache(m, 2, 32 if cfg.n_text_ctx >= 32 else cfg.n_text_ctx)
+    cache.set_encoder(enc.data_ptr())
+    nxt = None
+    for i, p in enumerate(cfg.prompt):
+        nxt, _ = m.decode_step(cache, [p, p], i)
+    out = [list(cfg.prompt) + [int(nxt[b])] for b in range(2)]
+    for _ in range(10):
+        start = cache.current_len - (1 if cfg.pos_quirk else 0)
+        nxt, lg = m.decode_step(cache, nxt, start, want_logits=True)
+        assert np.array_equal(lg.argmax(-1), nxt)
+        for b in range(2):
+            out[b].append(int(nxt[b]))
+    for b in range(2):
+        assert out[b] == [int(t) for t in toks[b, :len(out[b])]]
+    assert cache.current_len == 14
+
+
+def test_eot_stops_a_chunk():
+    """`if next_token == 50257: break` (whisper.mojo:206): make EOT the argmax by pointing its embedding
+    along the hidden state; the ids must end with EOT and later slots stay -1."""
+    cfg = WhisperConfig.micro()
+    w = synth.make_weights(cfg, seed=0)
+    om = O.OracleWhisper(cfg, w)
+    mel = synth.make_mel(2, cfg, 0)
+    ref0 = om.greedy(om.encode(mel[0]))
+    stop_tok = int(ref0[8])  # a token the greedy path emits: declare it to be EOT
+    cfg2 = WhisperConfig(**{**cfg.__dict__, "eot": stop_tok})
+    m = Whisper(cfg2)
+    m.load(WeightLoader(data=w))
+    toks, lens = m.transcribe_batch(mel)
+    ref = O.OracleWhisper(cfg2, w).greedy(om.encode(mel[0]))
+    assert ref[-1] == stop_tok and len(ref) < cfg.max_tokens
+    assert lens[0] == len(ref) and np.array_equal(toks[0, :lens[0]], ref) and np.all(toks[0, lens[0]:] == -1)
+
+
+def test_ops_engine_is_an_fp32_twin_of_the_oracle():
+    cfg = WhisperConfig.micro()
+    w = synth.make_weights(cfg, seed=0)
+    mel = synth.make_mel(1, cfg, 0)[0]
+    om = O.OracleWhisper(cfg, w)
+    mo = Whisper(cfg, engine="ops")
+    mo.load(WeightLoader(data=w))
+    enc = mo.encoder.forward(Tensor.from_numpy(mel)).numpy()
+    enc_ref, c1, c2 = om.encode(mel, taps=True)
+    assert np.abs(enc - enc_ref).max() <= 1e-4
+    assert mo.transcribe(mel) == [int(t) for t in om.greedy(enc_ref)]
+    # pos_quirk = 0 (HF positions) is honoured too
+    cfg0 = WhisperConfig(**{**cfg.__dict__, "pos_quirk": 0})
+    m0 = Whisper(cfg0, engine="ops")
+    m0.load(WeightLoader(data=w))
+    assert m0.transcribe(mel) == [int(t) for t in om.greedy(enc_ref, pos_quirk=0)]
+
+
+def test_pcm_entry_equals_logmel_then_transcribe():
+    cfg = WhisperConfig.tiny()
+    m, _ = build(cfg)
+    a = synth.make_audio(2, cfg, seed=5)
+    t1, l1 = m.transcribe_pcm_batch(a)
+    t2, l2 = m.transcribe_batch(m.log_mel(a))
+    assert np.array_equal(t1, t2) and np.array_equal(l1, l2)
+    tm = m.last_timing()
+    assert tm["encoder_ms"] > 0 and tm["decode_ms"] > 0
+    # device-resident entry points return CUDA tensors with the same ids
+    td, ld = m.transcribe_pcm_batch(torch.from_numpy(a).cuda())
+    assert td.is_cuda and np.array_equal(td.cpu().numpy(), t1) and np.array_equal(ld.cpu().numpy(), l1)
+
+
+def test_waves_and_encoder_sub_batches_do_not_change_results():
+    cfg = WhisperConfig.micro()
+    m, _ = build(cfg)
+    mel = synth.make_mel(7, cfg, 3)
+    t_all, l_all = m.transcribe_batch(mel)
+    m.set_option("wave_max", 3)
+    m.set_option("enc_batch", 2)
+    t_w, l_w = m.transcribe_batch(mel)
+    assert np.array_equal(t_all, t_w) and np.array_equal(l_all, l_w)
+
+
+def test_weight_loading_errors(tmp_path):
+    cfg = WhisperConfig.micro()
+    w = synth.make_weights(cfg, seed=0)
+    m = Whisper(cfg)
+    with pytest.raises(_lib.WhisperB200Error) as e:  # the reference reads past the end silently (loader.mojo:21-27)
+        m.load(WeightLoader(data=w[:-1]))
+    assert e.value.code == _lib.WB_ERR_IO
+    with pytest.raises(_lib.WhisperB200Error) as e:
+        m.transcribe_batch(synth.make_mel(1, cfg, 0))
+    assert "before weights are loaded" in str(e.value)
+    p = tmp_path / "w.bin"
+    synth.write_weights(str(p), w)
+    m.load_file(str(p))
+    m2, _ = build(cfg)
+    mel = synth.make_mel(1, cfg, 0)
+    assert np.array_equal(m.transcribe_batch(mel)[0], m2.transcribe_batch(mel)[0])
+    with pytest.raises(_lib.WhisperB200Error) as e:
+        Whisper(cfg).load_file(str(tmp_path / "missing.bin"))
+    assert e.value.code == _lib.WB_ERR_IO
+
+
+def test_small_shaped_config_runs_and_matches_oracle():
+    """BASELINE.json configs[4]: 12 layers, d=768, 12 heads; shortened decode to keep the oracle quick."""
+    base = WhisperConfig.small_shaped()
+    cfg = WhisperConfig(**{**base.__dict__, "max_iters": 12})
+    w = synth.make_weights(cfg, seed=1)
+    m = Whisper(cfg)
+    m.load(WeightLoader(data=w))
+    mel = synth.make_mel(2, cfg, 1)
+    om = O.OracleWhisper(cfg, w)
+    enc_ref = om.encode(mel[0])
+    enc = m.encode(mel[:1])[0]
+    assert np.abs(enc - enc_ref).max() <= 2 * ENC_MAX  # 12 layers deep
+    toks, lens = m.transcribe_batch(mel)
+    ref, mg = om.greedy(enc_ref, margins=True)
+    ok, msg = tokens_agree_up_to_margin(toks[0, :lens[0]], ref, mg, 2 * MARGIN_TAU)
+    assert ok, msg

@@ -1,0 +1,111 @@
+"""CPU: host-side logic -- synthetic assets, loader, tokenizer, sharding, and the world_size-2
+gather over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+from whisper_mojo_b200 import Tokenizer, WhisperConfig, synth
+from whisper_mojo_b200.dist import gather_tokens, shard_range
+
+
+def test_synth_weights_deterministic_and_sized():
+    cfg = WhisperConfig.micro()
+    a, b = synth.make_weights(cfg, seed=3), synth.make_weights(cfg, seed=3)
+    assert a.dtype == np.float32 and a.size == cfg.weight_count() and np.array_equal(a, b)
+    assert not np.array_equal(a, synth.make_weights(cfg, seed=4))
+    off, shape = cfg.weight_offsets()["enc.pos"]
+    assert np.allclose(a[off:off + shape[0] * shape[1]].reshape(shape), synth.sinusoids(*shape))
+
+
+def test_weight_file_roundtrip(tmp_path):
+    cfg = WhisperConfig.micro()
+    w = synth.make_weights(cfg, seed=0)
+    p = tmp_path / "w.bin"
+    synth.write_weights(str(p), w)
+    assert os.path.getsize(p) == 4 * cfg.weight_count()
+    assert np.array_equal(np.fromfile(p, "<f4"), w)
+
+
+def test_audio_shapes():
+    cfg = WhisperConfig.tiny()
+    a = synth.make_audio(2, cfg, seed=0)
+    assert a.shape == (2, 480000) and a.dtype == np.float32
+    assert np.abs(a[:, int(480000 * 0.8):]).max() < 1e-2  # quiet tail exercises the -8 clamp
+
+
+def test_tokenizer_matches_reference_rules(tmp_path):
+    p = tmp_path / "vocab.txt"
+    p.write_text("Hello\nĠworld\n<|endoftext|>\nline\\nbreak\n", encoding="utf-8")
+    t = Tokenizer(str(p))
+    assert t.decode([0, 1, 2, 3, 99, -1]) == "Hello worldline\nbreak"
+
+
+def test_tokenizer_on_reference_golden():
+    vocab = "/root/reference/vocab.txt"
+    if not os.path.exists(vocab):
+        pytest.skip("reference vocab not present on this machine")
+    import json
+
+    ids = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_expected_tokens.json")))["ids"]
+    text = Tokenizer(vocab).decode([50258, 50259, 50359, 50363] + ids + [50257])
+    assert text.startswith(" This is my voice on the left.") and text.endswith("out of phase on three.")
+
+
+@pytest.mark.parametrize("n,world", [(2048, 8), (2048, 1), (7, 4), (3, 8), (0, 2)])
+def test_shard_range_partitions(n, world):
+    parts = [shard_range(n, r, world) for r in range(world)]
+    assert parts[0][0] == 0 and parts[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(parts, parts[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [b - a for a, b in parts]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, n_total, T, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(n_total, rank, world)
+    toks = (torch.arange(lo, hi, dtype=torch.int32)[:, None] * 1000 + torch.arange(T, dtype=torch.int32)[None, :])
+    lens = torch.arange(lo, hi, dtype=torch.int32) % T + 1
+    out_t, out_l = gather_tokens(toks, lens, n_total, dst=0)
+    all_t, all_l = gather_tokens(toks, lens, n_total, dst=None)
+    ok = True
+    if rank == 0:
+        exp_t = (torch.arange(n_total, dtype=torch.int32)[:, None] * 1000 + torch.arange(T, dtype=torch.int32)[None, :])
+        exp_l = torch.arange(n_total, dtype=torch.int32) % T + 1
+        ok = torch.equal(out_t, exp_t) and torch.equal(out_l, exp_l)
+    else:
+        ok = out_t is None and out_l is None
+    ok = ok and all_t.shape == (n_total, T) and int(all_l[n_total - 1]) == (n_total - 1) % T + 1
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [5, 8])
+def test_gather_tokens_world2_gloo(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_total, 6, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

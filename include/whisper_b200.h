@@ -194,6 +194,10 @@ int wb_debug_gemm(int impl, const float *A_host, int batches, int src_rows, int 
 int wb_debug_decode_attention(const float *q_host, const float *K_host, const float *V_host, int B, int H, int len,
                               int splits, float *out_host);
 
+/* Test hook: encoder self-attention (layers.mojo:273-342, no mask) on host fp32 data rounded to bf16:
+ * qkv [B*S][3*D] (q | k | v) -> out [B*S][D].  impl: 0 CUDA-core kernel, 1 tcgen05 flash-attention kernel. */
+int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, int H, float *out_host);
+
 #ifdef __cplusplus
 }
 #endif

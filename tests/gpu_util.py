@@ -49,3 +49,12 @@ def tokens_agree_up_to_margin(got, ref, margins, tau):
         return False, f"prompt differs at {i}"
     low = np.nonzero(margins[: i - 4 + 1] < tau)[0]
     return len(low) > 0, f"first mismatch at {i}, oracle margin there {margins[i - 4]:.4f}, min margin before {margins[:i - 3].min():.4f}"
+
+
+def debug_encoder_attention(impl, qkv, B, S, H):
+    D = H * 64
+    qkv = np.ascontiguousarray(qkv, np.float32)
+    out = np.zeros((B * S, D), np.float32)
+    _lib.check(_lib.load().wb_debug_encoder_attention(impl, qkv.ctypes.data_as(c_void_p), B, S, H,
+                                                      out.ctypes.data_as(c_void_p)))
+    return out

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from gpu_util import bf16_round, debug_decode_attention, debug_gemm
+from gpu_util import bf16_round, debug_decode_attention, debug_encoder_attention, debug_gemm
 from oracle import logmel_oracle as LM
 from whisper_mojo_b200 import Whisper, WhisperConfig, synth
 
@@ -76,6 +76,23 @@ def test_decode_attention(B, H, ln, splits):
     p /= p.sum(-1, keepdims=True)
     ref = np.einsum("bhj,bjhd->bhd", p, Vh).reshape(B, D)
     assert np.abs(out - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max() / 2)  # bf16 output rounding
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 1500, 6), (1, 96, 2), (3, 128, 2), (2, 129, 2), (1, 300, 12), (2, 1, 2)])
+def test_encoder_attention_tc_vs_fp64(B, S, H):
+    """tcgen05 flash attention == softmax(q k^T / 8) v on the same bf16-rounded inputs; covers a ragged
+    last key block (1500 = 11*128 + 92), a single block, an exact multiple and S = 1."""
+    D = H * 64
+    qkv = bf16_round(rng.standard_normal((B * S, 3 * D), dtype=np.float32) * np.array([1.5] * (2 * D) + [1.0] * D, np.float32))
+    x = qkv.reshape(B, S, 3, H, 64).astype(np.float64)
+    s = np.einsum("bihd,bjhd->bhij", x[:, :, 0], x[:, :, 1]) * 0.125
+    p = np.exp(s - s.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    ref = np.einsum("bhij,bjhd->bihd", p, x[:, :, 2]).reshape(B * S, D)
+    for impl in (0, 1):
+        out = debug_encoder_attention(impl, qkv, B, S, H)
+        # P is rounded to bf16 before the PV product on the tensor-core path, outputs are bf16
+        assert np.abs(out - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max()), (impl, np.abs(out - ref).max())
 
 
 def test_logmel_frontend_matches_hf_golden_and_oracle():

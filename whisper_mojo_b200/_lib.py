@@ -73,6 +73,7 @@ SIGNATURES = {
     "wb_debug_gemm": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_int, c_void_p, c_int, c_void_p]),
     "wb_debug_decode_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "wb_debug_encoder_attention": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -688,4 +688,34 @@ int wb_debug_decode_attention(const float *q_host, const float *K_host, const fl
     return rc;
 }
 
+
+int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, int H, float *out_host) {
+    WB_ARG(qkv_host && out_host && B > 0 && S > 0 && H > 0, "debug_enc_attn: bad args");
+    WB_CHECK(need_device());
+    const int D = H * 64;
+    const size_t nin = (size_t)B * S * 3 * D, nout = (size_t)B * S * D;
+    float *f32 = nullptr;
+    __nv_bfloat16 *qkv = nullptr, *o = nullptr;
+    int rc = WB_OK;
+    auto ok = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == WB_OK) {
+            set_error("debug_enc_attn: %s", cudaGetErrorString(e));
+            rc = WB_ERR_CUDA;
+        }
+    };
+    ok(cudaMalloc((void **)&f32, nin * 4));
+    ok(cudaMalloc((void **)&qkv, nin * 2));
+    ok(cudaMalloc((void **)&o, nout * 2));
+    if (rc == WB_OK) ok(cudaMemcpy(f32, qkv_host, nin * 4, cudaMemcpyHostToDevice));
+    if (rc == WB_OK) rc = convert_f32_bf16(0, f32, qkv, nin);
+    if (rc == WB_OK) rc = impl ? encoder_attention_tc(0, qkv, o, B, S, H, D) : encoder_attention_ref(0, qkv, o, B, S, H, D);
+    if (rc == WB_OK) {
+        bf16_to_f32_kernel<<<(unsigned)((nout + 255) / 256), 256>>>(o, f32, nout);
+        ok(cudaGetLastError());
+        ok(cudaMemcpy(out_host, f32, nout * 4, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(f32), cudaFree(qkv), cudaFree(o);
+    return rc;
+}
+
 }  // extern "C"

@@ -1,0 +1,252 @@
+// attn_tc.cu -- encoder self-attention on tcgen05 tensor cores (sm_100a), flash-attention style.
+//
+// Replaces the reference's per-head gather -> QK^T -> scale -> softmax -> V^T -> PV -> scatter
+// (layers.mojo:273-342, no mask for the encoder) without ever materialising the 1500 x 1500 score
+// matrix.  One CTA = 128 queries of one (chunk, head); it walks the keys in blocks of 128:
+//
+//   warp 4  TMA producer : Q tile once, then K_j (2-deep ring) and V_j straight out of the fused
+//                          [tokens][3D] qkv activation (one 3-D tensor map; rows past the chunk's
+//                          1500 tokens are zero-filled by TMA, never read from the next chunk)
+//   warp 5  MMA issuer   : S = Q K_j^T  (UMMA 128x128x16, K-major x K-major) into TMEM cols [0,128)
+//                          O += P_j V_j (UMMA 128x64x16, P K-major from smem, V MN-major from smem)
+//                          into TMEM cols [128,192); S_{j+1} is issued before PV_j so it overlaps
+//                          the softmax of block j
+//   warps 0-3 softmax    : thread = query row; two passes over S in TMEM (max, then exp2 -> bf16 P
+//                          into 128B-swizzled smem), online-softmax rescale of O through
+//                          tcgen05.ld/st only when a row maximum moved
+//
+// 96 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's MMAs run
+// under the other's exponentials.  Output: O / l in bf16, one 128-byte row segment per thread.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100.cuh"
+
+namespace wb {
+
+int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                   uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
+
+static constexpr int ATT_THREADS = 192;
+static constexpr int TILE_BYTES = 128 * 64 * 2;  // 128 rows x 64 bf16
+static constexpr int ATT_SMEM = 1024 + 6 * TILE_BYTES + 256;  // Q, K0, K1, V, P_lo, P_hi + barriers
+
+struct AttnTcParams {
+    CUtensorMap qkv_map;  // dims (3D, S, B), box (64, 128, 1)
+    __nv_bfloat16 *out;   // [B*S][D]
+    int S, D, H, n_kblocks;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const __grid_constant__ AttnTcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = tiles, *sK = tiles + TILE_BYTES, *sV = tiles + 3 * TILE_BYTES, *sP = tiles + 4 * TILE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + 6 * TILE_BYTES);
+    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *s_full = bars + 6,
+             *s_empty = bars + 7, *p_full = bars + 8, *pv_done = bars + 9;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nblk = P.n_kblocks;
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tmap(&P.qkv_map);
+        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < 2; i++) ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
+        ptx::mbar_init(v_full, 1);
+        ptx::mbar_init(s_full, 1);
+        ptx::mbar_init(s_empty, 4);
+        ptx::mbar_init(p_full, 4);
+        ptx::mbar_init(pv_done, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 5) {
+        ptx::tmem_alloc(tmem_holder, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            ptx::mbar_expect_tx(q_full, TILE_BYTES);
+            ptx::tma_load_3d(sQ, &P.qkv_map, q_full, h * 64, q0, b);
+            auto load_k = [&](int j) {
+                const int s = j & 1;
+                ptx::mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+                ptx::mbar_expect_tx(&k_full[s], TILE_BYTES);
+                ptx::tma_load_3d(sK + s * TILE_BYTES, &P.qkv_map, &k_full[s], P.D + h * 64, j * 128, b);
+            };
+            load_k(0);
+            for (int j = 0; j < nblk; j++) {
+                if (j + 1 < nblk) load_k(j + 1);  // K runs one block ahead of V
+                if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);  // V buffer is free once PV_{j-1} has completed
+                ptx::mbar_expect_tx(v_full, TILE_BYTES);
+                ptx::tma_load_3d(sV, &P.qkv_map, v_full, 2 * P.D + h * 64, j * 128, b);
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
+            const uint64_t q_desc = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                ptx::mbar_wait(&k_full[s], (j >> 1) & 1);
+                ptx::mbar_wait(s_empty, (j & 1) ^ 1);  // softmax has drained S_{j-1} from TMEM
+                ptx::tc_fence_after();
+                const uint64_t k_desc = ptx::umma_desc_sw128(ptx::smem_u32(sK + s * TILE_BYTES), 1, 64);
+#pragma unroll
+                for (int k = 0; k < 4; k++) ptx::mma_bf16_ss(tS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+                ptx::mma_commit(&k_empty[s]);
+                ptx::mma_commit(s_full);
+            };
+            ptx::mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nblk; j++) {
+                if (j + 1 < nblk) issue_s(j + 1);
+                ptx::mbar_wait(p_full, j & 1);
+                ptx::mbar_wait(v_full, j & 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    // P: two 64-key sub-tiles, 32 B per 16-key step inside a sub-tile.
+                    const uint64_t p_desc =
+                        ptx::umma_desc_sw128(ptx::smem_u32(sP + (k >> 2) * TILE_BYTES), 1, 64) + 2 * (k & 3);
+                    // V (MN-major): 16 keys = two 8-row groups of 1024 B.
+                    const uint64_t v_desc = ptx::umma_desc_sw128(ptx::smem_u32(sV + k * 2048), 1, 64);
+                    ptx::mma_bf16_ss(tO, p_desc, v_desc, idesc_o, (j | k) != 0);
+                }
+                ptx::mma_commit(pv_done);
+            }
+        }
+    } else {
+        // ===== softmax warps: thread = query row (TMEM lane 32*warp + lane) =====
+        const int row = warp * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+        float m_run = -INFINITY, l_run = 0.f;
+        uint8_t *p_row = sP + row * 128;
+        const int sw = row & 7;
+        for (int j = 0; j < nblk; j++) {
+            const int kvalid = min(128, P.S - j * 128);  // keys of this block inside the chunk
+            ptx::mbar_wait(s_full, j & 1);
+            ptx::tc_fence_after();
+            // pass 1: row maximum
+            float m_blk = -INFINITY;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; cc++) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(tS + lane_addr + cc * 32, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 32; t++)
+                    if (cc * 32 + t < kvalid) m_blk = fmaxf(m_blk, __uint_as_float(v[t]));
+            }
+            const float m_new = fmaxf(m_run, m_blk);
+            const float alpha = exp2f((m_run - m_new) * c);  // 0 on the first block (m_run = -inf)
+            const float mc = m_new * c;
+            if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O holds blocks < j
+            // pass 2: p = exp2(s*c - m*c) -> bf16 -> swizzled smem (K-major A operand), row sum in fp32
+            float l_blk = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; cc++) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(tS + lane_addr + cc * 32, v);
+                ptx::tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    float p0 = (cc * 32 + t < kvalid) ? exp2f(__uint_as_float(v[t]) * c - mc) : 0.f;
+                    float p1 = (cc * 32 + t + 1 < kvalid) ? exp2f(__uint_as_float(v[t + 1]) * c - mc) : 0.f;
+                    l_blk += p0 + p1;
+                    pk[t >> 1] = pack_bf16x2(p0, p1);
+                }
+                // 32 keys = 4 chunks of 16 B; key index cc*32 .. -> sub-tile cc>>1, chunk (cc&1)*4 + i
+                uint8_t *dst = p_row + (cc >> 1) * TILE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int chunk = (cc & 1) * 4 + i;
+                    *reinterpret_cast<uint4 *>(dst + ((chunk ^ sw) << 4)) =
+                        make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+            }
+            // S_j is fully consumed: let the MMA warp overwrite it with S_{j+1}
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(s_empty);
+            l_run = l_run * alpha + l_blk;
+            m_run = m_new;
+            // rescale the running output when some row of this warp moved its maximum
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                for (int cc = 0; cc < 2; cc++) {
+                    uint32_t o[32];
+                    ptx::tmem_ld_32x32b_x32(tO + lane_addr + cc * 32, o);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int t = 0; t < 32; t++) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+                    ptx::tmem_st_32x32b_x32(tO + lane_addr + cc * 32, o);
+                }
+                ptx::tmem_st_wait();
+            }
+            ptx::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the MMA's async proxy
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(p_full);
+        }
+        // epilogue: O / l -> bf16 -> global
+        ptx::mbar_wait(pv_done, (nblk - 1) & 1);
+        ptx::tc_fence_after();
+        const float inv = 1.0f / l_run;
+        const int q = q0 + row;
+        __nv_bfloat16 *dst = P.out + ((size_t)b * P.S + q) * P.D + h * 64;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; cc++) {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32b_x32(tO + lane_addr + cc * 32, o);
+            ptx::tmem_ld_wait();
+            if (q < P.S) {
+#pragma unroll
+                for (int t = 0; t < 32; t += 8) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(o[t]) * inv, __uint_as_float(o[t + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(o[t + 2]) * inv, __uint_as_float(o[t + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(o[t + 4]) * inv, __uint_as_float(o[t + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(o[t + 6]) * inv, __uint_as_float(o[t + 7]) * inv);
+                    *reinterpret_cast<uint4 *>(dst + cc * 32 + t) = u;
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+int encoder_attention_tc(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D) {
+    if (B <= 0) return WB_OK;
+    WB_ARG(D == H * 64, "encoder_attention_tc: head_dim must be 64");
+    AttnTcParams P;
+    WB_CHECK(make_tmap_bf16(&P.qkv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D,
+                            (uint64_t)S * 3 * D, 128, 3));
+    P.out = out, P.S = S, P.D = D, P.H = H, P.n_kblocks = cdiv(S, 128);
+    static bool opted = false;
+    if (!opted) {
+        WB_CUDA(cudaFuncSetAttribute(encoder_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        opted = true;
+    }
+    dim3 grid(cdiv(S, 128), H, B);
+    encoder_attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(P);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+}  // namespace wb

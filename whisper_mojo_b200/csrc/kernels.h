@@ -40,6 +40,8 @@ int decode_attention_splits(int B, int len);
 // Encoder self-attention, bring-up implementation on CUDA cores (layers.mojo:273-342, no mask):
 // qkv bf16 [B*S][3D] -> out bf16 [B*S][D].
 int encoder_attention_ref(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D);
+// Same contract on tcgen05 tensor cores, flash-attention style (attn_tc.cu).
+int encoder_attention_tc(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D);
 
 // Greedy bookkeeping after a logits step (whisper.mojo:198-221): append next token unless the chunk
 // has finished, mark EOT, set the next input token, advance cur_len / pos.

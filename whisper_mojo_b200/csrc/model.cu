@@ -275,7 +275,8 @@ static int encode_batch(Model *m, const float *mel_dev, int n, float *enc_out_de
         const LayerDev &d = m->enc[l];
         WB_CHECK(ln_bf16(st, m->e_x, d.ln1_g, d.ln1_b, M, D, m->e_xn, nullptr));
         WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, m->e_qkv, 3 * D), impl));
-        WB_CHECK(encoder_attention_ref(st, m->e_qkv, m->e_attn, n, S, m->H, D));
+        if (m->attn_impl) WB_CHECK(encoder_attention_tc(st, m->e_qkv, m->e_attn, n, S, m->H, D));
+        else WB_CHECK(encoder_attention_ref(st, m->e_qkv, m->e_attn, n, S, m->H, D));
         WB_CHECK(gemm_run(st, plain_gemm(m->e_attn, M, D, d.wo, D, d.bo, EPI_RESID_F32, m->e_x, D), impl));
         WB_CHECK(ln_bf16(st, m->e_x, d.ln3_g, d.ln3_b, M, D, m->e_xn, nullptr));
         WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.w1, m->F, d.b1, EPI_GELU_BF16, m->e_h, m->F), impl));

@@ -52,7 +52,7 @@ struct Model {
     int D, H, L, V, S, T, NM, F, n_frames, n_samples;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int gemm_impl = 1, attn_impl = 0, use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048;
+    int gemm_impl = 1, attn_impl = 1, use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048;
     Layout lay;
     float *w32 = nullptr;
     bool loaded = false;

@@ -398,18 +398,28 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
 
 }  // extern "C"
 
-// Stage a host array on the device, run `fn(dev_in, dev_out)`, copy the result back.
+// Stage a host array on the device (grow-only buffers owned by the model), run `fn(dev_in, dev_out)`,
+// copy the result back.  The host pointers may be pageable or pinned; pinned makes the copies async DMA.
 template <typename Tin, typename Tout, typename Fn>
 static int staged(Model *m, const Tin *in_host, size_t n_in, Tout *out_host, size_t n_out, Fn fn) {
-    Tin *din = nullptr;
-    Tout *dout = nullptr;
+    auto grow = [&](void **p, size_t *cap, size_t bytes) {
+        if (*cap >= bytes) return true;
+        cudaFree(*p);
+        *p = nullptr, *cap = 0;
+        if (cudaMalloc(p, bytes) != cudaSuccess) {
+            set_error("staging allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+            return false;
+        }
+        *cap = bytes;
+        return true;
+    };
+    if (!grow(&m->stage_in, &m->stage_in_cap, std::max<size_t>(n_in, 1) * sizeof(Tin)) ||
+        !grow(&m->stage_out, &m->stage_out_cap, std::max<size_t>(n_out, 1) * sizeof(Tout)))
+        return WB_ERR_CUDA;
+    Tin *din = reinterpret_cast<Tin *>(m->stage_in);
+    Tout *dout = reinterpret_cast<Tout *>(m->stage_out);
     int rc = WB_OK;
-    if (cudaMalloc((void **)&din, std::max<size_t>(n_in, 1) * sizeof(Tin)) != cudaSuccess ||
-        cudaMalloc((void **)&dout, std::max<size_t>(n_out, 1) * sizeof(Tout)) != cudaSuccess) {
-        set_error("staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-        rc = WB_ERR_CUDA;
-    }
-    if (rc == WB_OK && cudaMemcpyAsync(din, in_host, n_in * sizeof(Tin), cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
+    if (cudaMemcpyAsync(din, in_host, n_in * sizeof(Tin), cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
         rc = WB_ERR_CUDA;
     if (rc == WB_OK) rc = fn(din, dout);
     if (rc == WB_OK &&
@@ -417,8 +427,6 @@ static int staged(Model *m, const Tin *in_host, size_t n_in, Tout *out_host, siz
         rc = WB_ERR_CUDA;
     if (rc == WB_OK && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = WB_ERR_CUDA;
     if (rc == WB_ERR_CUDA && g_err[0] == 0) set_error("CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(din);
-    cudaFree(dout);
     return rc;
 }
 

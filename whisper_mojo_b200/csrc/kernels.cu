@@ -4,6 +4,10 @@
 // size or position in the batch).
 #include "kernels.h"
 
+#include <math.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace wb {
@@ -245,12 +249,37 @@ __global__ void decode_attn_combine_kernel(const float *__restrict__ ws, __nv_bf
     *reinterpret_cast<uint32_t *>(out + (size_t)b * D + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
-int decode_attention_splits(int B, int len) {
-    int want = (592 + B - 1) / B;
-    int cap = len / 128;
-    if (cap < 1) cap = 1;
-    int s = want < cap ? want : cap;
-    return s < 1 ? 1 : s;
+// Split-K factor for a constant key length.  Every CTA streams the same number of K/V bytes, so the
+// kernel's efficiency is (CTAs / resident slots) / ceil(CTAs / resident slots): with one CTA per chunk
+// 2048 chunks over ~1000 slots is 2.05 waves -> 3 rounds.  Pick the smallest split count whose last
+// wave is >= 92 % full (or the best one), keeping at least 96 keys per split.
+int decode_attention_splits(int B, int len, int H) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int max_splits = len / 96;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 32) max_splits = 32;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= max_splits; s++) {
+        int chunk = ((len + s - 1) / s + 3) & ~3;
+        // resident CTAs per SM for this shared-memory footprint, from the occupancy calculator
+        size_t smem = (size_t)H * (chunk + 4) * sizeof(float);
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel, H * 32, smem) != cudaSuccess)
+            per_sm = 4, cudaGetLastError();
+        if (per_sm < 1) per_sm = 1;
+        double waves = (double)B * s / ((double)sms * per_sm);
+        double eff = waves / ceil(waves);
+        if (waves < 1.0) eff = waves;  // not even one full wave: more splits = more parallelism
+        eff *= 1.0 - 0.004 * (s - 1);  // fixed per-CTA cost (query load, softmax, partial write)
+        if (eff > best_eff + 1e-9) best_eff = eff, best = s;
+        if (eff >= 0.92) return s;
+    }
+    return best;
 }
 
 int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {

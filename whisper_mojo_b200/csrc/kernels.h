@@ -35,7 +35,7 @@ struct DecodeAttnArgs {
     float *ws;
 };
 int decode_attention(cudaStream_t st, const DecodeAttnArgs &a);
-int decode_attention_splits(int B, int len);
+int decode_attention_splits(int B, int len, int H);
 
 // Encoder self-attention, bring-up implementation on CUDA cores (layers.mojo:273-342, no mask):
 // qkv bf16 [B*S][3D] -> out bf16 [B*S][D].

@@ -119,6 +119,10 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
 void model_destroy(Model *m) {
     if (!m) return;
     cudaStreamSynchronize(m->stream);
+    if (m->tr_cache) cache_destroy(m->tr_cache);
+    cudaFree(m->tr_mel);
+    cudaFree(m->stage_in);
+    cudaFree(m->stage_out);
     for (void *p : m->owned) cudaFree(p);
     for (cudaEvent_t e : m->cross_timer.ev) cudaEventDestroy(e);
     frontend_tables_destroy(&m->ft);
@@ -318,7 +322,7 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, Cache **out) {
         return true;
     };
     const int tiles_n = gemm_tiles_n(m->V);
-    c->cross_splits = decode_attention_splits(B, m->S);
+    c->cross_splits = decode_attention_splits(B, m->S, m->H);
     bool ok = A(&c->self_kv, (size_t)m->L * 2 * B * max_len * D) && A(&c->cross_kv, (size_t)m->L * 2 * B * m->S * D) &&
               A(&c->x, B * D) && A(&c->xn, B * D) && A(&c->q, B * D) && A(&c->attn, B * D) &&
               A(&c->h, (size_t)B * m->F) && A(&c->part_val, (size_t)B * tiles_n) &&
@@ -509,16 +513,16 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
         size_t cap = std::max<size_t>(1, (free_b / 2) / per_chunk);
         wave = (int)std::min<size_t>(wave, cap);
     }
-    Cache *c = nullptr;
-    float *mel_tmp = nullptr;
+    Cache *c = m->tr_cache;  // reused across calls while the wave size stays the same
     int rc = WB_OK;
     for (int w0 = 0; w0 < n && rc == WB_OK; w0 += wave) {
         const int nb = std::min(wave, n - w0);
-        if (!c || c->B != nb) {
+        if (!c || c->B != nb || c->T != T_cache) {
             if (c) cache_destroy(c);
-            c = nullptr;
+            c = m->tr_cache = nullptr;
             rc = cache_create(m, nb, T_cache, false, &c);
             if (rc != WB_OK) break;
+            m->tr_cache = c;
         } else {
             rc = cache_reset(c);
             if (rc != WB_OK) break;
@@ -526,14 +530,19 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
         cudaEventRecord(ev[0], st);
         const float *mel_w = mel_dev ? mel_dev + w0 * mel_per : nullptr;
         if (!mel_dev) {  // frontend
-            if (!mel_tmp && cudaMalloc((void **)&mel_tmp, (size_t)wave * mel_per * 4) != cudaSuccess) {
-                set_error("transcribe: cannot allocate the log-mel buffer");
-                rc = WB_ERR_CUDA;
-                break;
+            if (m->tr_mel_cap < (size_t)wave * mel_per) {
+                cudaFree(m->tr_mel);
+                m->tr_mel = nullptr, m->tr_mel_cap = 0;
+                if (cudaMalloc((void **)&m->tr_mel, (size_t)wave * mel_per * 4) != cudaSuccess) {
+                    set_error("transcribe: cannot allocate the log-mel buffer");
+                    rc = WB_ERR_CUDA;
+                    break;
+                }
+                m->tr_mel_cap = (size_t)wave * mel_per;
             }
-            rc = model_logmel(m, pcm_dev + (size_t)w0 * m->n_samples, nb, mel_tmp);
+            rc = model_logmel(m, pcm_dev + (size_t)w0 * m->n_samples, nb, m->tr_mel);
             if (rc != WB_OK) break;
-            mel_w = mel_tmp;
+            mel_w = m->tr_mel;
         }
         cudaEventRecord(ev[1], st);
         rc = model_encode(m, mel_w, nb, nullptr, c, 0);
@@ -567,8 +576,6 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
             if (cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.total_ms += ms, t.launches++;
         }
     }
-    if (c) cache_destroy(c);
-    if (mel_tmp) cudaFree(mel_tmp);
     for (auto &e : ev) cudaEventDestroy(e);
     return rc;
 }

@@ -68,6 +68,12 @@ struct Model {
     float *e_x = nullptr;
     float timing[5] = {0, 0, 0, 0, 0};
     KernelTimer cross_timer;
+    // transcribe workspace kept across calls (allocation of a 19 GB cache costs ~0.2 s per call otherwise)
+    struct Cache *tr_cache = nullptr;
+    float *tr_mel = nullptr;
+    size_t tr_mel_cap = 0;
+    void *stage_in = nullptr, *stage_out = nullptr;  // host-API staging buffers (api.cu)
+    size_t stage_in_cap = 0, stage_out_cap = 0;
 };
 
 struct Cache {

@@ -187,6 +187,23 @@ def test_waves_and_encoder_sub_batches_do_not_change_results():
     assert np.array_equal(t_all, t_w) and np.array_equal(l_all, l_w)
 
 
+def test_two_decode_lanes_equal_one_lane():
+    """>= 256 chunks run as two half-batches on two streams inside one CUDA graph; ids must not change."""
+    cfg = WhisperConfig.micro()
+    m, _ = build(cfg)
+    mel = synth.make_mel(300, cfg, 11)
+    m.set_option("decode_lanes", 2)
+    t2, l2 = m.transcribe_batch(mel)
+    t2b, _ = m.transcribe_batch(mel)  # replay of the captured two-stream graph
+    m.set_option("decode_lanes", 1)
+    t1, l1 = m.transcribe_batch(mel)
+    assert np.array_equal(t1, t2) and np.array_equal(l1, l2) and np.array_equal(t2, t2b)
+    m.set_option("decode_lanes", 2)
+    m.set_option("use_graph", 0)
+    t3, _ = m.transcribe_batch(mel)
+    assert np.array_equal(t1, t3)
+
+
 def test_weight_loading_errors(tmp_path):
     cfg = WhisperConfig.micro()
     w = synth.make_weights(cfg, seed=0)

@@ -383,6 +383,14 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
     else if (!strcmp(key, "use_graph")) m->use_graph = (int)value;
     else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
+    else if (!strcmp(key, "decode_lanes")) {
+        WB_ARG(value == 1 || value == 2, "decode_lanes must be 1 or 2");
+        if (m->decode_lanes != (int)value && m->tr_cache) {
+            cache_destroy(m->tr_cache);
+            m->tr_cache = nullptr;
+        }
+        m->decode_lanes = (int)value;
+    }
     else if (!strcmp(key, "enc_batch")) {
         WB_ARG(value >= 1 && value <= 4096, "enc_batch out of range");
         m->enc_batch = (int)value;
@@ -462,7 +470,7 @@ int wm_kvcache_create(wm_model h, int n_chunks, int max_len, wm_cache *out) {
     MODEL(m, h);
     WB_ARG(out, "kvcache_create: null out");
     Cache *c = nullptr;
-    WB_CHECK(cache_create(m, n_chunks, max_len, true, &c));
+    WB_CHECK(cache_create(m, n_chunks, max_len, true, 1, &c));
     *out = put(g_caches, c);
     return WB_OK;
 }

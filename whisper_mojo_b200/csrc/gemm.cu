@@ -3,7 +3,8 @@
 // GEMM_IMPL_TC : persistent, warp-specialised sm_100a kernel.  One CTA per SM loops over 128x128
 //   output tiles; warp 0 feeds a 6-stage shared-memory ring with TMA (128-byte swizzle), warp 1
 //   issues tcgen05.mma (UMMA 128x128x16, bf16 -> fp32) into a double-buffered TMEM accumulator,
-//   warps 2..5 drain TMEM with tcgen05.ld and run the epilogue while the next tile's MMAs issue.
+//   warps 2..9 drain TMEM with tcgen05.ld (two warps per 32-lane quarter, 64 columns each) and run
+//   the epilogue while the next tile's MMAs issue.
 //   The conv stem runs through the same kernel as an implicit GEMM: the K loop walks 3 taps, each a
 //   TMA box shifted by one source row (zero fill outside the chunk = the conv's zero padding).
 // GEMM_IMPL_REF: plain CUDA-core kernel with the same operand / epilogue contract, used to
@@ -21,7 +22,8 @@ namespace wb {
 
 static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
 static constexpr int A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
-static constexpr int TC_THREADS = 192;
+static constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+static constexpr int PART_PER_TILE = 2;  // argmax partials per 128-column tile (one per epilogue column half)
 static constexpr int TC_SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
 
 // Device-visible parameters (shared by both implementations).
@@ -53,6 +55,15 @@ struct GemmTcParams {
     CUtensorMap b_map;
     GemmDev d;
 };
+
+// GELU for bf16 outputs: same formula as gelu_ref with the hardware tanh (MUFU.TANH, rel. error ~2^-11,
+// far below the bf16 rounding of the result).  fp32 outputs keep the exact tanhf.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float k0 = 0.79788456f, k1 = 0.044715f;
+    float inner = k0 * (x + k1 * x * x * x), t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+    return 0.5f * x * (1.0f + t);
+}
 
 // Resolve the output location of (global row, column n): returns element offset and segment.
 __device__ __forceinline__ void out_location(const GemmDev &p, long long grow, int n, int &seg, long long &off) {
@@ -179,7 +190,7 @@ __device__ __forceinline__ void epilogue_row32(const GemmDev &p, int b, int m, i
     if (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16) {
         if (EPI == EPI_GELU_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = gelu_ref(v[j]);
+            for (int j = 0; j < 32; j++) v[j] = gelu_fast(v[j]);
         }
         __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out[seg]) + off;
         if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
         for (int s = 0; s < 2; s++) {
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], 4);
+            ptx::mbar_init(&tmem_empty[s], 8);
         }
         ptx::fence_barrier_init();
     }
@@ -313,8 +324,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             }
         }
     } else {
-        // ===== epilogue warps (TMEM lanes 32*(warp%4) .. +31) =====
-        const int q = warp & 3;
+        // ===== epilogue warps: TMEM lanes 32*(warp%4) .. +31, columns 64*half .. +63 =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int acc = it & 1;
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             float best = -INFINITY;
             int best_idx = 0x7fffffff;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            for (int c = half * 2; c < half * 2 + 2; c++) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
                 ptx::tmem_ld_wait();
@@ -336,8 +347,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             }
             if (EPI == EPI_ARGMAX && m < p.rows_per_batch) {
                 long long grow = (long long)b * p.rows_per_batch + m;
-                p.part_val[grow * p.tiles_n + nt] = best;
-                p.part_idx[grow * p.tiles_n + nt] = best_idx;
+                p.part_val[(grow * p.tiles_n + nt) * PART_PER_TILE + half] = best;
+                p.part_idx[(grow * p.tiles_n + nt) * PART_PER_TILE + half] = best_idx;
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -519,11 +530,11 @@ int argmax_partials(cudaStream_t st, const float *part_val, const int *part_idx,
 
 __global__ void argmax_from_logits_kernel(const float *__restrict__ logits, int M, int N, int tiles_n,
                                           float *__restrict__ part_val, int *__restrict__ part_idx) {
-    int row = blockIdx.y, t = blockIdx.x, lane = threadIdx.x;
+    int row = blockIdx.y, t = blockIdx.x, lane = threadIdx.x;  // t = 64-column slot (PART_PER_TILE per 128-col tile)
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int j = lane; j < 128; j += 32) {
-        int n = t * 128 + j;
+    for (int j = lane; j < 64; j += 32) {
+        int n = t * 64 + j;
         if (n < N) {
             float v = logits[(size_t)row * N + n];
             if (v > best) best = v, bi = n;  // ascending n per lane: first max kept
@@ -539,9 +550,9 @@ __global__ void argmax_from_logits_kernel(const float *__restrict__ logits, int 
 }
 int argmax_partials_from_logits(cudaStream_t st, const float *logits, int M, int N, float *part_val, int *part_idx) {
     if (M <= 0) return WB_OK;
-    int tiles_n = gemm_tiles_n(N);
-    dim3 grid(tiles_n, M);
-    argmax_from_logits_kernel<<<grid, 32, 0, st>>>(logits, M, N, tiles_n, part_val, part_idx);
+    int slots = gemm_tiles_n(N);  // = PART_PER_TILE * ceil(N / 128)
+    dim3 grid(slots, M);
+    argmax_from_logits_kernel<<<grid, 32, 0, st>>>(logits, M, N, slots, part_val, part_idx);
     WB_LAUNCHED();
     return WB_OK;
 }

@@ -47,12 +47,13 @@ struct GemmDesc {
     const int *dyn_off = nullptr;  // device int; element offset added = (*dyn_off) * dyn_mult[s]
     int64_t dyn_mult[3] = {0, 0, 0};
     const float *pos = nullptr;  // EPI_GELU_POS_F32: [rows_per_batch][N]
-    float *part_val = nullptr;   // EPI_ARGMAX: [M][tiles_n]
+    float *part_val = nullptr;   // EPI_ARGMAX: [M][gemm_tiles_n(N)]
     int *part_idx = nullptr;
     float *logits = nullptr;  // EPI_ARGMAX: optional full logits [M][N]
 };
 
-static inline int gemm_tiles_n(int N) { return (N + 127) / 128; }
+// Number of argmax partial slots per row: two per 128-column tile (one per epilogue column half).
+static inline int gemm_tiles_n(int N) { return 2 * ((N + 127) / 128); }
 
 int gemm_run(cudaStream_t st, const GemmDesc &d, int impl);
 

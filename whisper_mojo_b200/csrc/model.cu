@@ -107,6 +107,13 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
         }
         m->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("wm_create: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        model_destroy(m);
+        return WB_ERR_CUDA;
+    }
     int rc = frontend_tables_create(&m->ft, m->NM);
     if (rc != WB_OK) {
         model_destroy(m);
@@ -126,6 +133,9 @@ void model_destroy(Model *m) {
     for (void *p : m->owned) cudaFree(p);
     for (cudaEvent_t e : m->cross_timer.ev) cudaEventDestroy(e);
     frontend_tables_destroy(&m->ft);
+    if (m->stream2) cudaStreamDestroy(m->stream2);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->own_stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -306,48 +316,79 @@ int model_encode(Model *m, const float *mel_dev, int n, float *enc_out_dev, Cach
 // ---------------------------------------------------------------------------------------------
 // KV cache (layers.mojo:14-69) and decode workspace
 // ---------------------------------------------------------------------------------------------
-int cache_create(Model *m, int B, int max_len, bool want_logits, Cache **out) {
+int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Cache **out) {
     WB_ARG(B > 0 && max_len > 0 && max_len <= m->T, "kvcache: bad size (B=%d max_len=%d n_text_ctx=%d)", B, max_len,
            m->T);
     Cache *c = new Cache();
     c->m = m, c->B = B, c->T = max_len;
     const size_t D = m->D;
+    bool ok = true;
     auto A = [&](auto **p, size_t n) {
         void *q = nullptr;
+        if (!ok) return;
         if (cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(**p)) != cudaSuccess) {
-            set_error("kvcache: cudaMalloc of %zu bytes failed", n * sizeof(**p));
-            return false;
+            set_error("kvcache: cudaMalloc of %zu bytes failed: %s", n * sizeof(**p),
+                      cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+            return;
         }
+        c->owned.push_back(q);
         *p = static_cast<std::remove_reference_t<decltype(*p)>>(q);
-        return true;
     };
-    const int tiles_n = gemm_tiles_n(m->V);
-    c->cross_splits = decode_attention_splits(B, m->S, m->H);
-    bool ok = A(&c->self_kv, (size_t)m->L * 2 * B * max_len * D) && A(&c->cross_kv, (size_t)m->L * 2 * B * m->S * D) &&
-              A(&c->x, B * D) && A(&c->xn, B * D) && A(&c->q, B * D) && A(&c->attn, B * D) &&
-              A(&c->h, (size_t)B * m->F) && A(&c->part_val, (size_t)B * tiles_n) &&
-              A(&c->part_idx, (size_t)B * tiles_n) && A(&c->next, B) &&
-              A(&c->attn_ws, (size_t)B * c->cross_splits * m->H * 66) &&
-              A(&c->g.tokens_out, (size_t)B * (5 + m->cfg.max_iters)) && A(&c->g.out_len, B) && A(&c->g.cur_tok, B) &&
-              A(&c->g.done, B) && A(&c->g.scalars, 4);
-    if (ok && (want_logits || m->gemm_impl == GEMM_IMPL_REF)) ok = A(&c->logits, (size_t)B * m->V);
-    if (ok && cudaMallocHost((void **)&c->pinned_scalars, 4 * sizeof(int)) != cudaSuccess) ok = false;
+    if (n_lanes < 1 || B < 256) n_lanes = 1;  // small batches are launch bound either way
+    if (n_lanes > 2) n_lanes = 2;
+    const int slots = gemm_tiles_n(m->V);
+    const int T_out = 5 + m->cfg.max_iters;
+    A(&c->self_kv, (size_t)m->L * 2 * B * max_len * D);
+    A(&c->cross_kv, (size_t)m->L * 2 * B * m->S * D);
+    A(&c->tokens_out, (size_t)B * T_out);
+    A(&c->out_len, B);
+    A(&c->cur_tok, B);
+    A(&c->done, B);
+    A(&c->scalars, 4 * n_lanes);
+    c->lanes.resize(n_lanes);
+    for (int i = 0; i < n_lanes && ok; i++) {
+        Lane &ln = c->lanes[i];
+        ln.b_off = (int)((int64_t)B * i / n_lanes);
+        ln.B = (int)((int64_t)B * (i + 1) / n_lanes) - ln.b_off;
+        ln.cross_splits = decode_attention_splits(ln.B, m->S, m->H);
+        A(&ln.x, ln.B * D);
+        A(&ln.xn, ln.B * D);
+        A(&ln.q, ln.B * D);
+        A(&ln.attn, ln.B * D);
+        A(&ln.h, (size_t)ln.B * m->F);
+        A(&ln.part_val, (size_t)ln.B * slots);
+        A(&ln.part_idx, (size_t)ln.B * slots);
+        A(&ln.next, ln.B);
+        A(&ln.attn_ws, (size_t)ln.B * ln.cross_splits * m->H * 66);
+        if (want_logits || m->gemm_impl == GEMM_IMPL_REF) A(&ln.logits, (size_t)ln.B * m->V);
+        ln.g.tokens_out = c->tokens_out + (size_t)ln.b_off * T_out;
+        ln.g.out_len = c->out_len + ln.b_off;
+        ln.g.cur_tok = c->cur_tok + ln.b_off;
+        ln.g.done = c->done + ln.b_off;
+        ln.g.scalars = c->scalars + 4 * i;
+        ln.g.T_out = T_out, ln.g.eot = m->cfg.eot, ln.g.pos_quirk = m->cfg.pos_quirk;
+    }
+    if (ok && cudaMallocHost((void **)&c->pinned_scalars, 8 * sizeof(int)) != cudaSuccess) {
+        set_error("kvcache: pinned allocation failed");
+        ok = false;
+    }
     if (!ok) {
         cache_destroy(c);
         return WB_ERR_CUDA;
     }
-    c->g.T_out = 5 + m->cfg.max_iters, c->g.eot = m->cfg.eot, c->g.pos_quirk = m->cfg.pos_quirk;
     *out = c;
     return cache_reset(c);
 }
 
 void cache_destroy(Cache *c) {
     if (!c) return;
-    if (c->m) cudaStreamSynchronize(c->m->stream);
+    if (c->m) {
+        cudaStreamSynchronize(c->m->stream);
+        cudaStreamSynchronize(c->m->stream2);
+    }
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    void *ptrs[] = {c->self_kv, c->cross_kv, c->x, c->xn, c->q, c->attn, c->h, c->part_val, c->part_idx, c->next,
-                    c->attn_ws, c->logits, c->g.tokens_out, c->g.out_len, c->g.cur_tok, c->g.done, c->g.scalars};
-    for (void *p : ptrs) cudaFree(p);
+    for (void *p : c->owned) cudaFree(p);
     if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
     delete c;
 }
@@ -356,7 +397,7 @@ int cache_reset(Cache *c) {
     Model *m = c->m;
     // the reference zero-fills its cache tensors (layers.mojo:30-36)
     WB_CUDA(cudaMemsetAsync(c->self_kv, 0, (size_t)m->L * 2 * c->B * c->T * m->D * sizeof(bf16), m->stream));
-    WB_CHECK(greedy_init(m->stream, c->g, c->B, m->cfg.prompt));
+    for (Lane &ln : c->lanes) WB_CHECK(greedy_init(m->stream, ln.g, ln.B, m->cfg.prompt));
     c->host_len = 0;
     c->has_cross = false;
     return WB_OK;
@@ -376,39 +417,40 @@ int cache_set_encoder(Cache *c, const float *enc_out_dev) {
     return WB_OK;
 }
 
-static int timed_cross_attention(Model *m, const DecodeAttnArgs &a) {
-    if (!m->profile_attn) return decode_attention(m->stream, a);
+static int timed_cross_attention(Model *m, cudaStream_t st, const DecodeAttnArgs &a) {
+    if (!m->profile_attn) return decode_attention(st, a);
     KernelTimer &t = m->cross_timer;
     while ((int)t.ev.size() < t.used + 2) {
         cudaEvent_t e;
         WB_CUDA(cudaEventCreate(&e));
         t.ev.push_back(e);
     }
-    WB_CUDA(cudaEventRecord(t.ev[t.used], m->stream));
-    int rc = decode_attention(m->stream, a);
-    WB_CUDA(cudaEventRecord(t.ev[t.used + 1], m->stream));
+    WB_CUDA(cudaEventRecord(t.ev[t.used], st));
+    int rc = decode_attention(st, a);
+    WB_CUDA(cudaEventRecord(t.ev[t.used + 1], st));
     t.used += 2;
     return rc;
 }
 
 // One decoder forward with q_len = 1 for every chunk of the cache (whisper.mojo:130-167,
 // layers.mojo:435-519 with is_decoder = True).  Token / position / cur_len come from device memory.
-int decode_step(Cache *c, bool with_logits, bool store_logits) {
+int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits) {
     Model *m = c->m;
-    cudaStream_t st = m->stream;
-    const int B = c->B, D = m->D, impl = m->gemm_impl;
+    const int B = ln.B, D = m->D, impl = m->gemm_impl;
     const float *W = m->w32;
-    int *cur_len = c->g.scalars, *pos = c->g.scalars + 1;
-    const size_t self_seg = (size_t)B * c->T * D, cross_seg = (size_t)B * m->S * D;
-    WB_CHECK(embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, c->g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
-                      m->dec[0].ln1_b, c->x, c->xn));
+    int *cur_len = ln.g.scalars, *pos = ln.g.scalars + 1;
+    // cache-wide segment sizes; this lane's chunks start b_off rows into every segment
+    const size_t self_seg = (size_t)c->B * c->T * D, cross_seg = (size_t)c->B * m->S * D;
+    const size_t self_off = (size_t)ln.b_off * c->T * D, cross_off = (size_t)ln.b_off * m->S * D;
+    WB_CHECK(embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, ln.g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
+                      m->dec[0].ln1_b, ln.x, ln.xn));
     for (int l = 0; l < m->L; l++) {
         const LayerDev &d = m->dec[l];
-        bf16 *sk = c->self_kv + (size_t)(l * 2) * self_seg, *sv = sk + self_seg;
-        bf16 *ck = c->cross_kv + (size_t)(l * 2) * cross_seg, *cv = ck + cross_seg;
-        if (l > 0) WB_CHECK(ln_bf16(st, c->x, d.ln1_g, d.ln1_b, B, D, c->xn, nullptr));
+        bf16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
+        bf16 *ck = c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off, *cv = ck + cross_seg;
+        if (l > 0) WB_CHECK(ln_bf16(st, ln.x, d.ln1_g, d.ln1_b, B, D, ln.xn, nullptr));
         {  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
-            GemmDesc g = plain_gemm(c->xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, c->q, D);
+            GemmDesc g = plain_gemm(ln.xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, ln.q, D);
             g.n_seg_ptrs = 3, g.seg_cols = D;
             g.out[1] = sk, g.out_ld[1] = (int64_t)c->T * D, g.dyn_mult[1] = D;
             g.out[2] = sv, g.out_ld[2] = (int64_t)c->T * D, g.dyn_mult[2] = D;
@@ -416,32 +458,32 @@ int decode_step(Cache *c, bool with_logits, bool store_logits) {
             WB_CHECK(gemm_run(st, g, impl));
         }
         DecodeAttnArgs a;
-        a.q = c->q, a.K = sk, a.V = sv, a.out = c->attn, a.kv_batch_stride = (int64_t)c->T * D;
+        a.q = ln.q, a.K = sk, a.V = sv, a.out = ln.attn, a.kv_batch_stride = (int64_t)c->T * D;
         a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
         a.splits = 1, a.ws = nullptr;
         WB_CHECK(decode_attention(st, a));
-        WB_CHECK(gemm_run(st, plain_gemm(c->attn, B, D, d.wo, D, d.bo, EPI_RESID_F32, c->x, D), impl));
+        WB_CHECK(gemm_run(st, plain_gemm(ln.attn, B, D, d.wo, D, d.bo, EPI_RESID_F32, ln.x, D), impl));
         // cross attention over the encoder positions (layers.mojo:463-488)
-        WB_CHECK(ln_bf16(st, c->x, d.ln2_g, d.ln2_b, B, D, c->xn, nullptr));
-        WB_CHECK(gemm_run(st, plain_gemm(c->xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, c->q, D), impl));
+        WB_CHECK(ln_bf16(st, ln.x, d.ln2_g, d.ln2_b, B, D, ln.xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, ln.q, D), impl));
         a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;
         a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
-        a.splits = c->cross_splits, a.ws = c->attn_ws;
-        WB_CHECK(timed_cross_attention(m, a));
-        WB_CHECK(gemm_run(st, plain_gemm(c->attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, c->x, D), impl));
+        a.splits = ln.cross_splits, a.ws = ln.attn_ws;
+        WB_CHECK(timed_cross_attention(m, st, a));
+        WB_CHECK(gemm_run(st, plain_gemm(ln.attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, ln.x, D), impl));
         // MLP (layers.mojo:490-517)
-        WB_CHECK(ln_bf16(st, c->x, d.ln3_g, d.ln3_b, B, D, c->xn, nullptr));
-        WB_CHECK(gemm_run(st, plain_gemm(c->xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, c->h, m->F), impl));
-        WB_CHECK(gemm_run(st, plain_gemm(c->h, B, m->F, d.w2, D, d.b2, EPI_RESID_F32, c->x, D), impl));
+        WB_CHECK(ln_bf16(st, ln.x, d.ln3_g, d.ln3_b, B, D, ln.xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, ln.h, m->F), impl));
+        WB_CHECK(gemm_run(st, plain_gemm(ln.h, B, m->F, d.w2, D, d.b2, EPI_RESID_F32, ln.x, D), impl));
     }
     if (with_logits) {  // whisper.mojo:156-166 + argmax :198,219
-        WB_CHECK(ln_bf16(st, c->x, W + m->lay.dec_ln_w, W + m->lay.dec_ln_b, B, D, c->xn, nullptr));
-        GemmDesc g = plain_gemm(c->xn, B, D, m->tok_emb_bf16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
-        g.part_val = c->part_val, g.part_idx = c->part_idx;
-        g.logits = (store_logits || impl == GEMM_IMPL_REF) ? c->logits : nullptr;
-        WB_ARG(!(store_logits || impl == GEMM_IMPL_REF) || c->logits, "decode_step: cache has no logits buffer");
+        WB_CHECK(ln_bf16(st, ln.x, W + m->lay.dec_ln_w, W + m->lay.dec_ln_b, B, D, ln.xn, nullptr));
+        GemmDesc g = plain_gemm(ln.xn, B, D, m->tok_emb_bf16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
+        g.part_val = ln.part_val, g.part_idx = ln.part_idx;
+        g.logits = (store_logits || impl == GEMM_IMPL_REF) ? ln.logits : nullptr;
+        WB_ARG(!(store_logits || impl == GEMM_IMPL_REF) || ln.logits, "decode_step: cache has no logits buffer");
         WB_CHECK(gemm_run(st, g, impl));
-        WB_CHECK(argmax_partials(st, c->part_val, c->part_idx, B, gemm_tiles_n(m->V), c->next));
+        WB_CHECK(argmax_partials(st, ln.part_val, ln.part_idx, B, gemm_tiles_n(m->V), ln.next));
     }
     return WB_OK;
 }
@@ -449,24 +491,44 @@ int decode_step(Cache *c, bool with_logits, bool store_logits) {
 // ---------------------------------------------------------------------------------------------
 // Whisper.transcribe (whisper.mojo:184-223), batched
 // ---------------------------------------------------------------------------------------------
+// One greedy step for every lane.  With two lanes the second one runs on stream2 between a fork and
+// a join event, so the same code serves eager execution and stream capture into one graph.
+static int step_all_lanes(Cache *c, bool with_logits, int mode, int next_prompt_token) {
+    Model *m = c->m;
+    const bool two = c->lanes.size() > 1;
+    if (two) {
+        WB_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+        WB_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+    }
+    for (size_t i = 0; i < c->lanes.size(); i++) {
+        Lane &ln = c->lanes[i];
+        cudaStream_t st = i == 0 ? m->stream : m->stream2;
+        WB_CHECK(decode_step(c, ln, st, with_logits, false));
+        WB_CHECK(greedy_advance(st, ln.g, ln.B, mode, next_prompt_token, ln.next));
+    }
+    if (two) {
+        WB_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+        WB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+    }
+    return WB_OK;
+}
+
 static int greedy_loop(Cache *c) {
     Model *m = c->m;
     cudaStream_t st = m->stream;
-    const int B = c->B;
+    const int n_lanes = (int)c->lanes.size();
     // prefill: the reference runs the 4 prompt ids as one q_len = 4 forward with a causal mask
     // (whisper.mojo:195-197); feeding them one by one through the cached step computes the same
     // thing (masked scores are exp(-1e10 - max) = 0 there) and only the last position's logits are used.
     for (int i = 0; i < 4; i++) {
-        WB_CHECK(decode_step(c, i == 3, false));
-        if (i < 3) WB_CHECK(greedy_advance(st, c->g, B, 0, m->cfg.prompt[i + 1], nullptr));
-        else WB_CHECK(greedy_advance(st, c->g, B, 1, 0, c->next));
+        if (i < 3) WB_CHECK(step_all_lanes(c, false, 0, m->cfg.prompt[i + 1]));
+        else WB_CHECK(step_all_lanes(c, true, 1, 0));
     }
     const bool graph = m->use_graph && !m->profile_attn;
     if (graph && !c->graph_exec) {
         cudaGraph_t gr = nullptr;
         WB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = decode_step(c, true, false);
-        if (rc == WB_OK) rc = greedy_advance(st, c->g, B, 1, 0, c->next);
+        int rc = step_all_lanes(c, true, 1, 0);
         cudaError_t e = cudaStreamEndCapture(st, &gr);
         if (rc != WB_OK) {
             if (gr) cudaGraphDestroy(gr);
@@ -478,16 +540,17 @@ static int greedy_loop(Cache *c) {
     }
     for (int it = 0; it < m->cfg.max_iters; it++) {  // whisper.mojo:205
         if ((it & 15) == 0) {                         // `if next_token == 50257: break`, polled every 16 steps
-            WB_CUDA(cudaMemcpyAsync(c->pinned_scalars, c->g.scalars, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            WB_CUDA(cudaMemcpyAsync(c->pinned_scalars, c->scalars, 4 * n_lanes * sizeof(int), cudaMemcpyDeviceToHost, st));
             WB_CUDA(cudaStreamSynchronize(st));
-            if (c->pinned_scalars[2] >= B) break;
+            int n_done = 0;
+            for (int i = 0; i < n_lanes; i++) n_done += c->pinned_scalars[4 * i + 2];
+            if (n_done >= c->B) break;
         }
         if (graph) {
             WB_CUDA(cudaGraphLaunch(c->graph_exec, st));
-            g_launches.fetch_add(12 * m->L + 4, std::memory_order_relaxed);  // kernels replayed by the graph
+            g_launches.fetch_add((12 * m->L + 4) * n_lanes, std::memory_order_relaxed);  // kernels replayed by the graph
         } else {
-            WB_CHECK(decode_step(c, true, false));
-            WB_CHECK(greedy_advance(st, c->g, B, 1, 0, c->next));
+            WB_CHECK(step_all_lanes(c, true, 1, 0));
         }
     }
     return WB_OK;
@@ -520,7 +583,7 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
         if (!c || c->B != nb || c->T != T_cache) {
             if (c) cache_destroy(c);
             c = m->tr_cache = nullptr;
-            rc = cache_create(m, nb, T_cache, false, &c);
+            rc = cache_create(m, nb, T_cache, false, m->decode_lanes, &c);
             if (rc != WB_OK) break;
             m->tr_cache = c;
         } else {
@@ -551,9 +614,9 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
         rc = greedy_loop(c);
         if (rc != WB_OK) break;
         cudaEventRecord(ev[3], st);
-        cudaMemcpyAsync(out_tokens_dev + (size_t)w0 * T_out, c->g.tokens_out, (size_t)nb * T_out * 4,
+        cudaMemcpyAsync(out_tokens_dev + (size_t)w0 * T_out, c->tokens_out, (size_t)nb * T_out * 4,
                         cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(out_len_dev + w0, c->g.out_len, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(out_len_dev + w0, c->out_len, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) {
             set_error("transcribe: %s", cudaGetErrorString(cudaGetLastError()));
             rc = WB_ERR_CUDA;
@@ -586,25 +649,28 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
 static int set_step_state(Cache *c, int cur_len, int pos, const int32_t *tokens_host) {
     Model *m = c->m;
     int sc[2] = {cur_len, pos};
-    WB_CUDA(cudaMemcpyAsync(c->g.scalars, sc, sizeof sc, cudaMemcpyHostToDevice, m->stream));
-    WB_CUDA(cudaMemcpyAsync(c->g.cur_tok, tokens_host, (size_t)c->B * 4, cudaMemcpyHostToDevice, m->stream));
+    WB_CUDA(cudaMemcpyAsync(c->lanes[0].g.scalars, sc, sizeof sc, cudaMemcpyHostToDevice, m->stream));
+    WB_CUDA(cudaMemcpyAsync(c->cur_tok, tokens_host, (size_t)c->B * 4, cudaMemcpyHostToDevice, m->stream));
     WB_CUDA(cudaStreamSynchronize(m->stream));  // sc is a stack variable
     return WB_OK;
 }
 
+// The step-wise entry points use caches created with a single lane.
 int cache_step_api(Cache *c, const int32_t *tokens_host, int start_pos, float *logits_host, int32_t *next_host) {
     Model *m = c->m;
     WB_ARG(m->loaded && c->has_cross, "decode_step: weights / encoder output not set");
+    WB_ARG(c->lanes.size() == 1, "decode_step: cache was not created through wm_kvcache_create");
     WB_ARG(tokens_host, "decode_step: null tokens");
     WB_ARG(c->host_len < c->T, "decode_step: cache full (%d)", c->T);
     WB_ARG(start_pos >= 0 && start_pos < m->T, "decode_step: start_pos %d out of range", start_pos);
-    WB_ARG(!logits_host || c->logits, "decode_step: cache was created without a logits buffer");
+    Lane &ln = c->lanes[0];
+    WB_ARG(!logits_host || ln.logits, "decode_step: cache was created without a logits buffer");
     WB_CHECK(set_step_state(c, c->host_len, start_pos, tokens_host));
-    WB_CHECK(decode_step(c, true, logits_host != nullptr));
+    WB_CHECK(decode_step(c, ln, m->stream, true, logits_host != nullptr));
     c->host_len++;
     if (logits_host)
-        WB_CUDA(cudaMemcpyAsync(logits_host, c->logits, (size_t)c->B * m->V * 4, cudaMemcpyDeviceToHost, m->stream));
-    if (next_host) WB_CUDA(cudaMemcpyAsync(next_host, c->next, (size_t)c->B * 4, cudaMemcpyDeviceToHost, m->stream));
+        WB_CUDA(cudaMemcpyAsync(logits_host, ln.logits, (size_t)c->B * m->V * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (next_host) WB_CUDA(cudaMemcpyAsync(next_host, ln.next, (size_t)c->B * 4, cudaMemcpyDeviceToHost, m->stream));
     WB_CUDA(cudaStreamSynchronize(m->stream));
     return WB_OK;
 }
@@ -615,18 +681,19 @@ int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_
     WB_ARG(n > 0 && n_forced >= 4 && n_forced <= m->T && enc_out_dev && forced_host && logits_host,
            "teacher_forced: bad arguments");
     Cache *c = nullptr;
-    WB_CHECK(cache_create(m, n, std::min(m->T, (n_forced + 7) & ~7), true, &c));
+    WB_CHECK(cache_create(m, n, std::min(m->T, (n_forced + 7) & ~7), true, 1, &c));
+    Lane &ln = c->lanes[0];
     int rc = cache_set_encoder(c, enc_out_dev);
     std::vector<int32_t> col(n);
     for (int i = 0; i < n_forced && rc == WB_OK; i++) {
         for (int b = 0; b < n; b++) col[b] = forced_host[(size_t)b * n_forced + i];
         const int pos = i < 4 ? i : i - m->cfg.pos_quirk;  // whisper.mojo:196,217
         rc = set_step_state(c, i, pos, col.data());
-        if (rc == WB_OK) rc = decode_step(c, i >= 3, i >= 3);
+        if (rc == WB_OK) rc = decode_step(c, ln, m->stream, i >= 3, i >= 3);
         if (rc == WB_OK && i >= 3) {
             // logits_host is [n][n_forced-3][V]; this step is row i-3 of every chunk
             cudaError_t e = cudaMemcpy2DAsync(logits_host + (size_t)(i - 3) * m->V,
-                                              (size_t)(n_forced - 3) * m->V * 4, c->logits, (size_t)m->V * 4,
+                                              (size_t)(n_forced - 3) * m->V * 4, ln.logits, (size_t)m->V * 4,
                                               (size_t)m->V * 4, n, cudaMemcpyDeviceToHost, m->stream);
             if (e != cudaSuccess || cudaStreamSynchronize(m->stream) != cudaSuccess) {
                 set_error("teacher_forced: copy failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -50,9 +50,11 @@ struct KernelTimer {
 struct Model {
     wm_config cfg;
     int D, H, L, V, S, T, NM, F, n_frames, n_samples;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second decode lane
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
-    int gemm_impl = 1, attn_impl = 1, use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048;
+    int gemm_impl = 1, attn_impl = 1, use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048,
+        decode_lanes = 1;  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
     Layout lay;
     float *w32 = nullptr;
     bool loaded = false;
@@ -76,6 +78,18 @@ struct Model {
     size_t stage_in_cap = 0, stage_out_cap = 0;
 };
 
+// A lane = a contiguous sub-batch of the cache's chunks with its own decode workspace and step state.
+// Two lanes run on two streams inside one CUDA graph: one lane's small latency-bound kernels overlap the
+// other lane's HBM-bound cross-attention.
+struct Lane {
+    int B = 0, b_off = 0;
+    float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr;
+    bf16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr;
+    int *part_idx = nullptr, *next = nullptr;
+    int cross_splits = 1;
+    GreedyState g;  // per-chunk arrays point into the cache-wide arrays at b_off; scalars are per lane
+};
+
 struct Cache {
     Model *m = nullptr;
     int B = 0, T = 0;
@@ -83,12 +97,9 @@ struct Cache {
     bool has_cross = false;
     bf16 *self_kv = nullptr;   // [L][2][B][T][D]
     bf16 *cross_kv = nullptr;  // [L][2][B][S][D]
-    // decode workspace
-    float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr;
-    bf16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr;
-    int *part_idx = nullptr, *next = nullptr;
-    int cross_splits = 1;
-    GreedyState g;
+    int *tokens_out = nullptr, *out_len = nullptr, *cur_tok = nullptr, *done = nullptr, *scalars = nullptr;
+    std::vector<Lane> lanes;
+    std::vector<void *> owned;
     int *pinned_scalars = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
 };
@@ -98,11 +109,11 @@ void model_destroy(Model *m);
 int model_load(Model *m, const float *host, int64_t n_floats);
 int model_logmel(Model *m, const float *pcm_dev, int n, float *mel_dev);
 int model_encode(Model *m, const float *mel_dev, int n, float *enc_out_dev, Cache *into, int cache_off);
-int cache_create(Model *m, int B, int max_len, bool want_logits, Cache **out);
+int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Cache **out);
 void cache_destroy(Cache *c);
 int cache_reset(Cache *c);
 int cache_set_encoder(Cache *c, const float *enc_out_dev);
-int decode_step(Cache *c, bool with_logits, bool store_logits);
+int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits);
 int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
                      int32_t *out_len_dev);
 int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_t *forced_host, int n_forced,

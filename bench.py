@@ -178,8 +178,8 @@ def ncu_traffic(chunks):
     """dram__bytes_read.sum + dram__bytes_write.sum per cross-attention launch from the committed
     `ncu --set full` capture (profiles/), valid for the chunk count it was captured at; else None."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_decode_attn_ncu_full.json")))
-        if d["algorithmic_bytes_per_launch"] == chunks * (2 * 1500 * 384 + 2 * 384) * 2:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_cross_attn_absorbed_ncu_full.json")))
+        if d["algorithmic_bytes_per_launch"] == chunks * (1500 * 384 + 2 * 6 * 384) * 2:
             return d["cross_attention_traffic_bytes_per_launch"]
     except Exception:
         pass
@@ -292,13 +292,14 @@ def run_b200(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # algorithmic bytes per launch: every chunk's cross K and V of one layer (bf16) read once,
-        # plus the query and output rows: B * (2*S*D + 2*D) * 2 bytes   (e_kv = 2)
-        alg = C * (2 * cfg.n_audio_ctx * cfg.d_model + 2 * cfg.d_model) * 2
+        # algorithmic bytes per launch of the absorbed cross-attention: every chunk's bf16 enc_out read once
+        # (it stands in for both K and V of the layer), plus the folded queries and the per-head contexts:
+        # B * (S*D + 2*H*D) * 2 bytes.  (The K/V-cache form, cross_impl=0, reads B * (2*S*D + 2*D) * 2.)
+        alg = C * (cfg.n_audio_ctx * cfg.d_model + 2 * cfg.n_heads * cfg.d_model) * 2
         if n_launch > 0:
             avg_ms = tot_ms / n_launch
             ach = alg / (avg_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "decode_attn_kernel (cross-attention, one layer, one step)",
+            roofline = {"bound": "hbm", "kernel": "cross_attn_absorbed_kernel (cross-attention of one layer, one decode step)",
                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s",
                         "traffic": ncu_traffic(C), "avg_launch_ms": avg_ms, "launches_timed": n_launch,

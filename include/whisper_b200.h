@@ -124,7 +124,9 @@ int wm_load_weights(wm_model m, const float *host, int64_t n_floats);
  * index (0 .. n_tensors-1); what WeightLoader.next_tensor hands out. */
 int wm_weight_tensor(wm_model m, int index, void **dev_ptr, int64_t *n_floats);
 
-/* Select kernels: 0 = CUDA-core bring-up kernels, 1 = tcgen05/TMA kernels (default). */
+/* Options: "gemm_impl" / "attn_impl" 0 = CUDA-core bring-up kernels, 1 = tcgen05/TMA kernels (default);
+ * "cross_impl" 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (default when
+ * d_model <= 384); "use_graph", "decode_lanes", "enc_batch", "wave_max", "profile_attn". */
 int wm_set_option(wm_model m, const char *key, int64_t value);
 
 /* Log-mel frontend (HF WhisperFeatureExtractor via export_weights.py:116): pcm f32 [n_chunks,
@@ -197,6 +199,11 @@ int wb_debug_decode_attention(const float *q_host, const float *K_host, const fl
 /* Test hook: encoder self-attention (layers.mojo:273-342, no mask) on host fp32 data rounded to bf16:
  * qkv [B*S][3*D] (q | k | v) -> out [B*S][D].  impl: 0 CUDA-core kernel, 1 tcgen05 flash-attention kernel. */
 int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, int H, float *out_host);
+
+/* Test hook: absorbed cross-attention (cross_attn_tc.cu) on host fp32 data rounded to bf16:
+ * qp [B][H*D] (scores are used in base 2: p = 2^(s - max)), enc [B][S][D] -> ctx [B][H*D]. */
+int wb_debug_cross_attention_absorbed(const float *qp_host, const float *enc_host, int B, int S, int D, int H,
+                                      float *ctx_host);
 
 #ifdef __cplusplus
 }

@@ -58,3 +58,13 @@ def debug_encoder_attention(impl, qkv, B, S, H):
     _lib.check(_lib.load().wb_debug_encoder_attention(impl, qkv.ctypes.data_as(c_void_p), B, S, H,
                                                       out.ctypes.data_as(c_void_p)))
     return out
+
+
+def debug_cross_attention_absorbed(qp, enc, H):
+    B, S, D = enc.shape
+    qp = np.ascontiguousarray(qp, np.float32)
+    enc = np.ascontiguousarray(enc, np.float32)
+    out = np.zeros((B, H * D), np.float32)
+    _lib.check(_lib.load().wb_debug_cross_attention_absorbed(qp.ctypes.data_as(c_void_p), enc.ctypes.data_as(c_void_p),
+                                                             B, S, D, H, out.ctypes.data_as(c_void_p)))
+    return out

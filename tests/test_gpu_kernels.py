@@ -7,7 +7,8 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from gpu_util import bf16_round, debug_decode_attention, debug_encoder_attention, debug_gemm
+from gpu_util import (bf16_round, debug_cross_attention_absorbed, debug_decode_attention, debug_encoder_attention,
+                      debug_gemm)
 from oracle import logmel_oracle as LM
 from whisper_mojo_b200 import Whisper, WhisperConfig, synth
 
@@ -93,6 +94,23 @@ def test_encoder_attention_tc_vs_fp64(B, S, H):
         out = debug_encoder_attention(impl, qkv, B, S, H)
         # P is rounded to bf16 before the PV product on the tensor-core path, outputs are bf16
         assert np.abs(out - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max()), (impl, np.abs(out - ref).max())
+
+
+@pytest.mark.parametrize("B,S,D,H", [(3, 1500, 384, 6), (1, 96, 128, 2), (2, 128, 128, 2), (5, 129, 256, 4), (300, 200, 384, 6),
+                                     (2, 1, 128, 2)])
+def test_cross_attention_absorbed_vs_fp64(B, S, D, H):
+    """ctx[b][h] = sum_j softmax2_j(q'_h . enc_j) enc_j (base-2 softmax: log2(e)/8 is folded into q');
+    covers the ragged last key block, a single block, more chunks than SMs and S = 1."""
+    qp = bf16_round(rng.standard_normal((B, H * D), dtype=np.float32) * 0.15)
+    enc = bf16_round(rng.standard_normal((B, S, D), dtype=np.float32))
+    out = debug_cross_attention_absorbed(qp, enc, H)
+    q = qp.reshape(B, H, D).astype(np.float64)
+    e = enc.astype(np.float64)
+    s = np.einsum("bhc,bjc->bhj", q, e)
+    p = np.exp2(s - s.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    ref = np.einsum("bhj,bjc->bhc", p, e).reshape(B, H * D)
+    assert np.abs(out - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max()), np.abs(out - ref).max()
 
 
 def test_logmel_frontend_matches_hf_golden_and_oracle():

@@ -187,6 +187,25 @@ def test_waves_and_encoder_sub_batches_do_not_change_results():
     assert np.array_equal(t_all, t_w) and np.array_equal(l_all, l_w)
 
 
+def test_kv_cache_cross_attention_form_still_matches_oracle(setup):
+    """cross_impl = 0 keeps the reference's formulation (per-layer cross K/V cache); the default absorbed
+    form and this one must both satisfy the oracle bounds and agree with each other on clear steps."""
+    cfg, mel, m, om, enc_ref = setup
+    m0, _ = build(cfg, cross_impl=0)
+    t0, l0 = m0.transcribe_batch(mel)
+    for i in range(len(mel)):
+        ref, mg = om.greedy(enc_ref[i], margins=True)
+        ok, msg = tokens_agree_up_to_margin(t0[i, :l0[i]], ref, mg, MARGIN_TAU)
+        assert ok, f"chunk {i}: {msg}"
+    forced = np.stack([np.concatenate([np.array(cfg.prompt), np.random.default_rng(20 + i).integers(0, cfg.vocab_size, 8)])
+                       for i in range(len(mel))]).astype(np.int32)
+    enc = torch.from_numpy(enc_ref).cuda()
+    la, lb = m.teacher_forced(enc, forced), m0.teacher_forced(enc, forced)
+    ref = np.stack([om.teacher_forced(enc_ref[i], forced[i]) for i in range(len(mel))])
+    assert np.abs(la - ref).max() <= LOGIT_MAX and np.abs(lb - ref).max() <= LOGIT_MAX
+    assert np.abs(la - lb).max() <= LOGIT_MAX
+
+
 def test_two_decode_lanes_equal_one_lane():
     """>= 256 chunks run as two half-batches on two streams inside one CUDA graph; ids must not change."""
     cfg = WhisperConfig.micro()

@@ -1,0 +1,11 @@
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+os.environ["WB_XA_DBG"] = "1"
+from gpu_util import debug_cross_attention_absorbed, bf16_round
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+rng = np.random.default_rng(0)
+qp = (rng.standard_normal((B, 6 * 384), dtype=np.float32) * 0.15)
+enc = rng.standard_normal((B, 1500, 384), dtype=np.float32)
+debug_cross_attention_absorbed(qp, enc, 6)

@@ -74,6 +74,7 @@ SIGNATURES = {
                               c_int, c_void_p, c_int, c_void_p]),
     "wb_debug_decode_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "wb_debug_encoder_attention": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "wb_debug_cross_attention_absorbed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

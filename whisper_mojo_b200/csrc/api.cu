@@ -1,6 +1,7 @@
 // api.cu -- the C ABI declared in include/whisper_b200.h: handle tables, argument validation and
 // host<->device staging around model.cu / ops.cu.  No C++ type or exception crosses this file.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -383,7 +384,11 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
     else if (!strcmp(key, "use_graph")) m->use_graph = (int)value;
     else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
-    else if (!strcmp(key, "decode_lanes")) {
+    else if (!strcmp(key, "cross_impl")) {
+        WB_ARG(value == 0 || (value == 1 && cross_attn_absorbed_supported(m->D, m->H)),
+               "cross_impl must be 0, or 1 with d_model <= 384");
+        m->cross_impl = (int)value;
+    } else if (!strcmp(key, "decode_lanes")) {
         WB_ARG(value == 1 || value == 2, "decode_lanes must be 1 or 2");
         if (m->decode_lanes != (int)value && m->tr_cache) {
             cache_destroy(m->tr_cache);
@@ -731,6 +736,69 @@ int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, in
         ok(cudaMemcpy(out_host, f32, nout * 4, cudaMemcpyDeviceToHost));
     }
     cudaFree(f32), cudaFree(qkv), cudaFree(o);
+    return rc;
+}
+
+
+int wb_debug_cross_attention_absorbed(const float *qp_host, const float *enc_host, int B, int S, int D, int H,
+                                      float *ctx_host) {
+    WB_ARG(qp_host && enc_host && ctx_host && B > 0 && S > 0 && H > 0, "debug_cross_absorbed: bad args");
+    WB_CHECK(need_device());
+    const size_t nq = (size_t)B * H * D, ne = (size_t)B * S * D;
+    float *f32 = nullptr;
+    __nv_bfloat16 *qp = nullptr, *enc = nullptr, *ctx = nullptr;
+    int rc = WB_OK;
+    auto ok = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == WB_OK) {
+            set_error("debug_cross_absorbed: %s", cudaGetErrorString(e));
+            rc = WB_ERR_CUDA;
+        }
+    };
+    ok(cudaMalloc((void **)&f32, std::max(nq, ne) * 4));
+    ok(cudaMalloc((void **)&qp, nq * 2));
+    ok(cudaMalloc((void **)&enc, ne * 2));
+    ok(cudaMalloc((void **)&ctx, nq * 2));
+    if (rc == WB_OK) ok(cudaMemcpy(f32, qp_host, nq * 4, cudaMemcpyHostToDevice));
+    if (rc == WB_OK) rc = convert_f32_bf16(0, f32, qp, nq);
+    if (rc == WB_OK) ok(cudaDeviceSynchronize());
+    if (rc == WB_OK) ok(cudaMemcpy(f32, enc_host, ne * 4, cudaMemcpyHostToDevice));
+    if (rc == WB_OK) rc = convert_f32_bf16(0, f32, enc, ne);
+    if (rc == WB_OK) rc = cross_attention_absorbed(0, qp, enc, ctx, B, S, D, H);
+    if (rc == WB_OK && getenv("WB_XA_DBG")) {  // timestamp dump of CTA 0 (development aid)
+        unsigned long long *d = nullptr;
+        const size_t nd = 3 * 64 * 8;
+        ok(cudaMalloc((void **)&d, nd * 8));
+        ok(cudaMemset(d, 0, nd * 8));
+        g_xa_dbg = d;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        cudaEventRecord(e0, 0);
+        rc = cross_attention_absorbed(0, qp, enc, ctx, B, S, D, H);
+        cudaEventRecord(e1, 0);
+        g_xa_dbg = nullptr;
+        ok(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        std::vector<unsigned long long> h(nd);
+        ok(cudaMemcpy(h.data(), d, nd * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = h[0];
+        fprintf(stderr, "XA kernel %.3f ms (B=%d)\nblk | tma_issue | mma: enc_full s_empty p_full c_commit | smx: s_full ld_done max_done bar1 pre_cdone post_cdone p_stored p_arrive  (us)\n", ms, B);
+        const int order[8] = {0, 4, 5, 6, 1, 2, 7, 3};
+        for (int g = 0; g < 30; g++) {
+            fprintf(stderr, "%3d | %8.2f |", g, (h[(0 * 64 + g) * 8 + 0] - t0) / 1e3);
+            for (int e = 0; e < 4; e++) fprintf(stderr, " %8.2f", (h[(1 * 64 + g) * 8 + e] - t0) / 1e3);
+            fprintf(stderr, " |");
+            for (int e = 0; e < 8; e++) fprintf(stderr, " %8.2f", (h[(2 * 64 + g) * 8 + order[e]] - t0) / 1e3);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(d);
+    }
+    if (rc == WB_OK) {
+        bf16_to_f32_kernel<<<(unsigned)((nq + 255) / 256), 256>>>(ctx, f32, nq);
+        ok(cudaGetLastError());
+        ok(cudaMemcpy(ctx_host, f32, nq * 4, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(f32), cudaFree(qp), cudaFree(enc), cudaFree(ctx);
     return rc;
 }
 

@@ -1,0 +1,379 @@
+// cross_attn_tc.cu -- decode-step cross-attention over the encoder output itself ("absorbed" form).
+//
+// The reference keeps per-layer cross K = enc*Wk^T and V = enc*Wv^T + bv (layers.mojo:148-157) and the
+// decode step reads both (2 x 1500 x D values per chunk per layer, layers.mojo:186-272).  Since
+//     q_h . K_j,h  = (Wk_h^T q_h) . enc_j          and     sum_j p_j V_j,h = Wv_h (sum_j p_j enc_j) + bv_h
+// every head can attend over enc_out directly: Wk is folded into the query projection and Wv into
+// the output projection at load time (model.cu), and this kernel reads each chunk's enc_out ONCE per
+// layer -- half the HBM bytes of the K/V form, and the cache shrinks from L*2 tensors to 1 per chunk.
+//
+// One persistent CTA per SM walks chunks; per chunk it streams enc_out in blocks of 128 keys:
+//   warp 4  TMA     : Q' tile [16 x D] (heads padded to 16 rows by TMA zero fill) and the
+//                     [128 keys x D] block as D/64 swizzled [128 x 64] atoms, 2-stage ring
+//   warp 5  MMA (scores) : S[128 keys x 16 heads]   = enc_blk (A, K-major)   x Q'^T (B, K-major)    N = 16
+//   warp 6  MMA (context): C[D x 16 heads]         += enc_blk^T (A, MN-major) x P^T (B, K-major)     N = 16
+//                     (keys are the UMMA M dimension, so the 6 heads cost N = 16, not M = 128; the 48
+//                     small MMAs per block are issue bound, hence two issuing threads in parallel)
+//   warps 0-3 softmax: thread = key; per-head max / sum across the 128 threads (shuffles + smem),
+//                     online-softmax rescale of C through tcgen05.ld/st when a head's max moved,
+//                     P^T written to swizzled smem; at the end C / l -> bf16 ctx [B][H*D]
+// Scores arrive already multiplied by log2(e)/8 (folded into Wqk), so p = exp2(s - m).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100.cuh"
+
+namespace wb {
+
+int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                   uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
+
+static constexpr int XA_THREADS = 224;
+static constexpr int ATOM_BYTES = 128 * 64 * 2;  // [128 keys x 64 channels] bf16
+static constexpr int QATOM_BYTES = 16 * 64 * 2;  // [16 heads x 64 channels]
+static constexpr int XA_MAX_ATOMS = 6;           // D <= 384
+
+struct CrossAttnParams {
+    CUtensorMap enc_map;  // dims (D, S, B), box (64, 128, 1)
+    CUtensorMap q_map;    // dims (D, H, B), box (64, 16, 1): rows >= H are zero filled
+    __nv_bfloat16 *ctx;   // [B][H*D]
+    int B, S, D, H, n_blocks, atoms;
+    unsigned long long *dbg;  // optional timestamp dump (CTA 0): [role][block][event]
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+#define XA_STAMP(role, blk, ev)                                                              \
+    do {                                                                                     \
+        if (P.dbg && blockIdx.x == 0 && (blk) < 64) P.dbg[((role)*64 + (blk)) * 8 + (ev)] = ptx::globaltimer_ns(); \
+    } while (0)
+
+template <int ATOMS>
+__global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(const __grid_constant__ CrossAttnParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int atoms = ATOMS;
+    constexpr int stage_bytes = atoms * ATOM_BYTES;
+    uint8_t *sEnc = base;                                  // [2][atoms][128 x 64]
+    uint8_t *sQ = base + 2 * stage_bytes;                  // [atoms][16 x 64]
+    uint8_t *sP = sQ + XA_MAX_ATOMS * QATOM_BYTES;         // [2][16 x 64]   P^T, keys 0-63 | 64-127
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * QATOM_BYTES);
+    uint64_t *enc_full = bars, *enc_empty = bars + 2, *q_full = bars + 4, *q_empty = bars + 5, *s_full = bars + 6,
+             *s_empty = bars + 8, *p_full = bars + 10, *c_done = bars + 11, *c_empty = bars + 12;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 13);
+    float *s_red = reinterpret_cast<float *>(bars + 14);  // [4 warps][16] cross-warp reduction scratch
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = P.n_blocks, D = P.D;
+    constexpr int H = ATOMS;  // head_dim = 64, so H = D / 64 = number of 64-channel atoms
+    constexpr int n_acc = ATOMS / 2;  // C accumulators of [128 channels x 16 heads]
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tmap(&P.enc_map);
+        ptx::prefetch_tmap(&P.q_map);
+        for (int i = 0; i < 2; i++) {
+            ptx::mbar_init(&enc_full[i], 1);
+            ptx::mbar_init(&enc_empty[i], 1);
+            ptx::mbar_init(&s_full[i], 1);
+            ptx::mbar_init(&s_empty[i], 4);
+        }
+        ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(q_empty, 1);
+        ptx::mbar_init(p_full, 4);
+        ptx::mbar_init(c_done, 1);
+        ptx::mbar_init(c_empty, 4);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 5) {
+        ptx::tmem_alloc(tmem_holder, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    // TMEM columns: score partials S[stage][part] @ 16 * (stage * n_acc + part) (< 96), context C_m @ 128 + 32 m.
+    // Back-to-back MMAs into one accumulator serialise (~45 ns each), so the K = D reduction of the scores is
+    // split into one partial accumulator per atom pair and the issue order interleaves accumulators.
+    const uint32_t tS0 = tmem_base, tC0 = tmem_base + 128;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int g = 0, ci = 0;  // g: global block counter of this CTA, ci: chunk counter
+            for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+                ptx::mbar_wait(q_empty, (ci & 1) ^ 1);  // score MMAs of the previous chunk are done with sQ
+                ptx::mbar_expect_tx(q_full, atoms * QATOM_BYTES);
+                for (int a = 0; a < atoms; a++) ptx::tma_load_3d(sQ + a * QATOM_BYTES, &P.q_map, q_full, a * 64, 0, b);
+                for (int j = 0; j < nblk; j++, g++) {
+                    const int s = g & 1;
+                    ptx::mbar_wait(&enc_empty[s], ((g >> 1) & 1) ^ 1);
+                    XA_STAMP(0, g, 0);
+                    ptx::mbar_expect_tx(&enc_full[s], stage_bytes);
+                    for (int a = 0; a < atoms; a++)
+                        ptx::tma_load_3d(sEnc + s * stage_bytes + a * ATOM_BYTES, &P.enc_map, &enc_full[s], a * 64,
+                                         j * 128, b);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer 1: scores =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 16, 0, 0);  // enc (K-major) x Q' (K-major)
+            uint64_t a_desc0[2], b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
+            for (int s = 0; s < 2; s++) a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), 1, 64);
+            int g = 0, ci = 0;
+            for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+                ptx::mbar_wait(q_full, ci & 1);
+                for (int j = 0; j < nblk; j++, g++) {
+                    const int s = g & 1;
+                    ptx::mbar_wait(&enc_full[s], (g >> 1) & 1);
+                    XA_STAMP(1, g, 0);
+                    ptx::mbar_wait(&s_empty[s], ((g >> 1) & 1) ^ 1);
+                    XA_STAMP(1, g, 1);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++) {  // 8 K-steps of 16 channels inside an atom pair
+#pragma unroll
+                        for (int part = 0; part < n_acc; part++) {
+                            const int a = 2 * part + (kk >> 2), k = kk & 3;  // descriptors advance in 16-byte units
+                            ptx::mma_bf16_ss(tS0 + 16 * (s * n_acc + part), a_desc0[s] + a * (ATOM_BYTES >> 4) + 2 * k,
+                                             b_desc0 + a * (QATOM_BYTES >> 4) + 2 * k, idesc_s, kk != 0);
+                        }
+                    }
+                    ptx::mma_commit(&s_full[s]);
+                    if (j + 1 == nblk) ptx::mma_commit(q_empty);
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===== MMA issuer 2: context =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_c = ptx::umma_idesc_bf16(128, 16, 1, 0);  // enc^T (MN-major) x P^T (K-major)
+            uint64_t a_desc0[2];
+            // A = enc_blk^T: channels [128 m, 128 m + 128) = atoms 2m, 2m+1 (LBO = one atom),
+            // K = keys: 8-row groups 1024 B apart, 16 keys per MMA = 2048 B
+            for (int s = 0; s < 2; s++)
+                a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), ATOM_BYTES >> 4, 64);
+            const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sP), 1, 64);
+            int g = 0, ci = 0;
+            for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+                ptx::mbar_wait(c_empty, (ci & 1) ^ 1);  // epilogue of the previous chunk has drained C
+                for (int j = 0; j < nblk; j++, g++) {
+                    const int s = g & 1;
+                    ptx::mbar_wait(p_full, g & 1);  // softmax(g) done => scores(g) done reading the stage too
+                    XA_STAMP(1, g, 2);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+#pragma unroll
+                        for (int m = 0; m < n_acc; m++)  // consecutive MMAs hit different accumulators
+                            ptx::mma_bf16_ss(tC0 + 32 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
+                                             p_desc0 + (k >> 2) * (QATOM_BYTES >> 4) + 2 * (k & 3), idesc_c, (j | k) != 0);
+                    }
+                    ptx::mma_commit(&enc_empty[s]);
+                    ptx::mma_commit(c_done);
+                    XA_STAMP(1, g, 3);
+                }
+            }
+        }
+    } else {
+        // ===== softmax / correction / epilogue warps =====
+        const int row = warp * 32 + lane;  // key within the block, and channel lane for C
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        for (int i = row; i < 2 * QATOM_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0, 0, 0, 0);
+        ptx::fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        int g = 0, ci = 0;
+        for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+            float m_run[H], l_part[H];
+#pragma unroll
+            for (int h = 0; h < H; h++) m_run[h] = -INFINITY, l_part[h] = 0.f;
+            for (int j = 0; j < nblk; j++, g++) {
+                const int s = g & 1;
+                const bool valid = j * 128 + row < P.S;
+                ptx::mbar_wait(&s_full[s], (g >> 1) & 1);
+                if (threadIdx.x == 0) XA_STAMP(2, g, 0);
+                ptx::tc_fence_after();
+                uint32_t sv[16], sv1[16], sv2[16];
+                tmem_ld_32x32b_x16(tS0 + 16 * (s * n_acc) + lane_addr, sv);
+                if (n_acc > 1) tmem_ld_32x32b_x16(tS0 + 16 * (s * n_acc + 1) + lane_addr, sv1);
+                if (n_acc > 2) tmem_ld_32x32b_x16(tS0 + 16 * (s * n_acc + 2) + lane_addr, sv2);
+                ptx::tmem_ld_wait();
+                if (threadIdx.x == 0) XA_STAMP(2, g, 4);
+#pragma unroll
+                for (int h = 0; h < H; h++) {
+                    float v = __uint_as_float(sv[h]);
+                    if (n_acc > 1) v += __uint_as_float(sv1[h]);
+                    if (n_acc > 2) v += __uint_as_float(sv2[h]);
+                    sv[h] = __float_as_uint(v);
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&s_empty[s]);
+                // per-head maximum over the 128 keys of the block: butterfly steps outermost so the H independent
+                // shuffles of a step pipeline (head-outermost compiles to 5 x H serially dependent SHFLs)
+                float sc[H], mx[H];
+#pragma unroll
+                for (int h = 0; h < H; h++) mx[h] = sc[h] = valid ? __uint_as_float(sv[h]) : -INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int h = 0; h < H; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
+                }
+                if (lane < H) {
+                    float v = mx[0];
+#pragma unroll
+                    for (int h = 1; h < H; h++)
+                        if (lane == h) v = mx[h];
+                    s_red[warp * 16 + lane] = v;
+                }
+                if (threadIdx.x == 0) XA_STAMP(2, g, 5);
+                named_bar_sync(1, 128);
+                if (threadIdx.x == 0) XA_STAMP(2, g, 6);
+                float alpha[H];
+                bool moved = false;
+#pragma unroll
+                for (int h = 0; h < H; h++) {
+                    float mb = fmaxf(fmaxf(s_red[h], s_red[16 + h]), fmaxf(s_red[32 + h], s_red[48 + h]));
+                    float mn = fmaxf(m_run[h], mb);
+                    alpha[h] = exp2f(m_run[h] - mn);  // 0 on the first block
+                    moved |= (alpha[h] != 1.0f);
+                    m_run[h] = mn;
+                }
+                // P^T[h][key] = exp2(s - m) in bf16, 128B-swizzled rows of 64 keys
+                if (threadIdx.x == 0) XA_STAMP(2, g, 1);
+                if (g > 0) ptx::mbar_wait(c_done, (g - 1) & 1);  // previous block's C MMAs done: sP free, C stable
+                if (threadIdx.x == 0) XA_STAMP(2, g, 2);
+                {
+                    uint8_t *atom = sP + (row >> 6) * QATOM_BYTES;
+                    const int kk = row & 63;
+#pragma unroll
+                    for (int h = 0; h < H; h++) {  // rows of the padded heads (h >= H) were zeroed once at kernel start
+                        float p = valid ? exp2f(sc[h] - m_run[h]) : 0.f;
+                        l_part[h] = l_part[h] * alpha[h] + p;
+                        *reinterpret_cast<__nv_bfloat16 *>(atom + h * 128 + (((kk >> 3) ^ (h & 7)) << 4) + (kk & 7) * 2) =
+                            __float2bfloat16(p);
+                    }
+                }
+                // rescale the running context when a head's maximum moved (uniform across the CTA)
+                if (j > 0 && moved) {
+                    for (int m = 0; m < n_acc; m++) {
+                        uint32_t cv[16];
+                        tmem_ld_32x32b_x16(tC0 + 32 * m + lane_addr, cv);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int h = 0; h < H; h++) cv[h] = __float_as_uint(__uint_as_float(cv[h]) * alpha[h]);
+                        tmem_st_32x32b_x16(tC0 + 32 * m + lane_addr, cv);
+                    }
+                    ptx::tmem_st_wait();
+                }
+                if (threadIdx.x == 0) XA_STAMP(2, g, 7);
+                ptx::fence_proxy_async_smem();
+                ptx::tc_fence_before();
+                named_bar_sync(2, 128);  // all four warps are past their s_red reads before the next block writes it
+                if (lane == 0) ptx::mbar_arrive(p_full);
+                if (threadIdx.x == 0) XA_STAMP(2, g, 3);
+            }
+            // ---- chunk epilogue: l[h] = sum over the 128 threads; ctx = C / l ----
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int h = 0; h < H; h++) l_part[h] += __shfl_xor_sync(0xffffffffu, l_part[h], o);
+            }
+            if (lane < H) {
+                float v = l_part[0];
+#pragma unroll
+                for (int h = 1; h < H; h++)
+                    if (lane == h) v = l_part[h];
+                s_red[warp * 16 + lane] = v;
+            }
+            named_bar_sync(1, 128);
+            float inv[H];
+#pragma unroll
+            for (int h = 0; h < H; h++) inv[h] = 1.0f / (s_red[h] + s_red[16 + h] + s_red[32 + h] + s_red[48 + h]);
+            ptx::mbar_wait(c_done, (g - 1) & 1);
+            ptx::tc_fence_after();
+            __nv_bfloat16 *dst = P.ctx + (size_t)b * H * D;
+            for (int m = 0; m < n_acc; m++) {
+                uint32_t cv[16];
+                tmem_ld_32x32b_x16(tC0 + 32 * m + lane_addr, cv);
+                ptx::tmem_ld_wait();
+                const int c = m * 128 + row;
+#pragma unroll
+                for (int h = 0; h < H; h++) dst[(size_t)h * D + c] = __float2bfloat16(__uint_as_float(cv[h]) * inv[h]);
+            }
+            ptx::tc_fence_before();
+            named_bar_sync(2, 128);
+            if (lane == 0) ptx::mbar_arrive(c_empty);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+size_t cross_attn_absorbed_smem(int D) {
+    const int atoms = D / 64;
+    return 1024 + (size_t)2 * atoms * ATOM_BYTES + XA_MAX_ATOMS * QATOM_BYTES + 2 * QATOM_BYTES + 14 * 8 + 64 * 4 + 64;
+}
+
+bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 384 && H <= 16; }
+
+// q' bf16 [B][H*D] (already scaled by log2(e)/8 through the folded weights), enc bf16 [B][S][D]
+// -> ctx bf16 [B][H*D] with ctx[b][h] = softmax_j(q'_h . enc_j) weighted sum of enc_j.
+unsigned long long *g_xa_dbg = nullptr;  // set by the debug hook to collect timestamps
+
+int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __nv_bfloat16 *enc, __nv_bfloat16 *ctx,
+                             int B, int S, int D, int H) {
+    if (B <= 0) return WB_OK;
+    WB_ARG(cross_attn_absorbed_supported(D, H) && H * 64 == D,
+           "absorbed cross-attention needs head_dim 64, D %% 128 == 0, D <= 384 (D=%d H=%d)", D, H);
+    CrossAttnParams P;
+    WB_CHECK(make_tmap_bf16(&P.enc_map, enc, (uint64_t)D, (uint64_t)S, (uint64_t)B, (uint64_t)D, (uint64_t)S * D, 128, 3));
+    WB_CHECK(make_tmap_bf16(&P.q_map, qp, (uint64_t)D, (uint64_t)H, (uint64_t)B, (uint64_t)D, (uint64_t)H * D, 16, 3));
+    P.ctx = ctx, P.B = B, P.S = S, P.D = D, P.H = H, P.n_blocks = cdiv(S, 128), P.atoms = D / 64;
+    P.dbg = g_xa_dbg;
+    const size_t smem = cross_attn_absorbed_smem(D);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = B < sms ? B : sms;
+    static bool opted[3] = {false, false, false};
+    auto launch = [&](auto kernel, int slot) {
+        if (!opted[slot]) {
+            WB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            opted[slot] = true;
+        }
+        kernel<<<grid, XA_THREADS, smem, st>>>(P);
+        WB_LAUNCHED();
+        return WB_OK;
+    };
+    switch (P.atoms) {
+        case 2: return launch(cross_attn_absorbed_kernel<2>, 0);
+        case 4: return launch(cross_attn_absorbed_kernel<4>, 1);
+        default: return launch(cross_attn_absorbed_kernel<6>, 2);
+    }
+}
+
+}  // namespace wb

@@ -457,4 +457,55 @@ int convert_conv_weight(cudaStream_t st, const float *w, __nv_bfloat16 *dst, int
     return WB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Folding of the cross-attention projections (see kernels.h); one thread per output element.
+// ---------------------------------------------------------------------------------------------
+__global__ void fold_qk_kernel(const float *__restrict__ Wq, const float *__restrict__ bq,
+                               const float *__restrict__ Wk, int D, int H, __nv_bfloat16 *__restrict__ Wqk,
+                               float *__restrict__ bqk) {
+    const float alpha = 0.125f * 1.4426950408889634f;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)H * D * (D + 1);  // last column of each row = bias
+    if (idx >= n) return;
+    int i = (int)(idx % (D + 1));
+    int hc = (int)(idx / (D + 1));
+    int h = hc / D, c = hc % D;
+    float acc = 0.f;
+    for (int d = 0; d < 64; d++) {
+        float wk = Wk[(size_t)(h * 64 + d) * D + c];
+        acc += wk * (i < D ? Wq[(size_t)(h * 64 + d) * D + i] : bq[h * 64 + d]);
+    }
+    if (i < D) Wqk[(size_t)hc * D + i] = __float2bfloat16(acc * alpha);
+    else bqk[hc] = acc * alpha;
+}
+__global__ void fold_ov_kernel(const float *__restrict__ Wv, const float *__restrict__ bv,
+                               const float *__restrict__ Wo, const float *__restrict__ bo, int D, int H,
+                               __nv_bfloat16 *__restrict__ Wov, float *__restrict__ bov) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)D * (H * D + 1);
+    if (idx >= n) return;
+    int col = (int)(idx % ((size_t)H * D + 1));
+    int row = (int)(idx / ((size_t)H * D + 1));
+    if (col < H * D) {
+        int h = col / D, c = col % D;
+        float acc = 0.f;
+        for (int d = 0; d < 64; d++) acc += Wo[(size_t)row * D + h * 64 + d] * Wv[(size_t)(h * 64 + d) * D + c];
+        Wov[(size_t)row * H * D + col] = __float2bfloat16(acc);
+    } else {
+        float acc = bo[row];
+        for (int j = 0; j < D; j++) acc += Wo[(size_t)row * D + j] * bv[j];
+        bov[row] = acc;
+    }
+}
+int fold_cross_weights(cudaStream_t st, const float *Wq, const float *bq, const float *Wk, const float *Wv,
+                       const float *bv, const float *Wo, const float *bo, int D, int H, __nv_bfloat16 *Wqk,
+                       float *bqk, __nv_bfloat16 *Wov, float *bov) {
+    size_t n1 = (size_t)H * D * (D + 1), n2 = (size_t)D * ((size_t)H * D + 1);
+    fold_qk_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(Wq, bq, Wk, D, H, Wqk, bqk);
+    WB_LAUNCHED();
+    fold_ov_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(Wv, bv, Wo, bo, D, H, Wov, bov);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
 }  // namespace wb

@@ -43,6 +43,19 @@ int encoder_attention_ref(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat
 // Same contract on tcgen05 tensor cores, flash-attention style (attn_tc.cu).
 int encoder_attention_tc(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D);
 
+// Decode cross-attention over enc_out itself (cross_attn_tc.cu): q' bf16 [B][H*D], enc bf16 [B][S][D]
+// -> ctx bf16 [B][H*D].  Needs the folded weights below.
+int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __nv_bfloat16 *enc, __nv_bfloat16 *ctx,
+                             int B, int S, int D, int H);
+bool cross_attn_absorbed_supported(int D, int H);
+extern unsigned long long *g_xa_dbg;  // development aid: timestamp buffer for CTA 0 (normally null)
+// Load-time folding (fp32 math, bf16 result):
+//   Wqk[h*D + c][i] = (log2(e)/8) * sum_d Wk[h*64+d][c] * Wq[h*64+d][i],  bqk[h*D + c] = (log2(e)/8) * sum_d Wk[h*64+d][c] * bq[h*64+d]
+//   Wov[n][h*D + c] = sum_d Wo[n][h*64+d] * Wv[h*64+d][c],                  bov[n] = bo[n] + sum_j Wo[n][j] * bv[j]
+int fold_cross_weights(cudaStream_t st, const float *Wq, const float *bq, const float *Wk, const float *Wv,
+                       const float *bv, const float *Wo, const float *bo, int D, int H, __nv_bfloat16 *Wqk,
+                       float *bqk, __nv_bfloat16 *Wov, float *bov);
+
 // Greedy bookkeeping after a logits step (whisper.mojo:198-221): append next token unless the chunk
 // has finished, mark EOT, set the next input token, advance cur_len / pos.
 struct GreedyState {

@@ -96,6 +96,7 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
     m->S = cfg->n_audio_ctx, m->T = cfg->n_text_ctx, m->NM = cfg->n_mels, m->F = 4 * cfg->d_model;
     m->n_frames = 2 * m->S, m->n_samples = m->n_frames * 160;
     m->lay = make_layout(*cfg);
+    if (!cross_attn_absorbed_supported(m->D, m->H)) m->cross_impl = 0;
     if (stream) {
         m->stream = reinterpret_cast<cudaStream_t>(stream);
     } else {
@@ -202,6 +203,16 @@ int model_load(Model *m, const float *host, int64_t n_floats) {
                 WB_CHECK(convert_f32_bf16(st, W + b.cross.v_w, m->cross_wkv + (size_t)(i * 2 + 1) * DD, DD));
                 WB_CUDA(cudaMemcpyAsync(m->cross_bkv + (size_t)(i * 2 + 1) * D, W + b.cross.v_b, (size_t)D * 4,
                                         cudaMemcpyDeviceToDevice, st));
+                if (cross_attn_absorbed_supported(D, m->H)) {
+                    const size_t HD = (size_t)m->H * D;
+                    WB_CHECK(dalloc(m, &d.wqk, HD * D));
+                    WB_CHECK(dalloc(m, &d.bqk, HD));
+                    WB_CHECK(dalloc(m, &d.wov, HD * D));
+                    WB_CHECK(dalloc(m, &d.bov, (size_t)D));
+                    WB_CHECK(fold_cross_weights(st, W + b.cross.q_w, W + b.cross.q_b, W + b.cross.k_w, W + b.cross.v_w,
+                                                W + b.cross.v_b, W + b.cross.o_w, W + b.cross.o_b, D, m->H, d.wqk, d.bqk,
+                                                d.wov, d.bov));
+                }
             }
         }
     }
@@ -296,6 +307,12 @@ static int encode_batch(Model *m, const float *mel_dev, int n, float *enc_out_de
         WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.w1, m->F, d.b1, EPI_GELU_BF16, m->e_h, m->F), impl));
         WB_CHECK(gemm_run(st, plain_gemm(m->e_h, M, m->F, d.w2, D, d.b2, EPI_RESID_F32, m->e_x, D), impl));
     }
+    if (into && into->cross_impl == 1) {
+        // absorbed form: the bf16 encoder output IS the cross-attention cache (one tensor for all layers)
+        WB_CHECK(ln_bf16(st, m->e_x, W + m->lay.enc_ln_w, W + m->lay.enc_ln_b, M, D,
+                         into->cross_enc + (size_t)cache_off * S * D, enc_out_dev));
+        return WB_OK;
+    }
     WB_CHECK(ln_bf16(st, m->e_x, W + m->lay.enc_ln_w, W + m->lay.enc_ln_b, M, D, m->e_enc, enc_out_dev));
     if (into) WB_CHECK(cross_kv_project(m, m->e_enc, n, into, cache_off));
     return WB_OK;
@@ -340,7 +357,9 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
     const int slots = gemm_tiles_n(m->V);
     const int T_out = 5 + m->cfg.max_iters;
     A(&c->self_kv, (size_t)m->L * 2 * B * max_len * D);
-    A(&c->cross_kv, (size_t)m->L * 2 * B * m->S * D);
+    c->cross_impl = m->cross_impl;
+    if (c->cross_impl == 1) A(&c->cross_enc, (size_t)B * m->S * D);
+    else A(&c->cross_kv, (size_t)m->L * 2 * B * m->S * D);
     A(&c->tokens_out, (size_t)B * T_out);
     A(&c->out_len, B);
     A(&c->cur_tok, B);
@@ -361,6 +380,10 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
         A(&ln.part_idx, (size_t)ln.B * slots);
         A(&ln.next, ln.B);
         A(&ln.attn_ws, (size_t)ln.B * ln.cross_splits * m->H * 66);
+        if (c->cross_impl == 1) {
+            A(&ln.qp, (size_t)ln.B * m->H * D);
+            A(&ln.ctx, (size_t)ln.B * m->H * D);
+        }
         if (want_logits || m->gemm_impl == GEMM_IMPL_REF) A(&ln.logits, (size_t)ln.B * m->V);
         ln.g.tokens_out = c->tokens_out + (size_t)ln.b_off * T_out;
         ln.g.out_len = c->out_len + ln.b_off;
@@ -407,6 +430,11 @@ int cache_set_encoder(Cache *c, const float *enc_out_dev) {
     Model *m = c->m;
     WB_ARG(m->loaded, "kvcache_set_encoder before weights are loaded");
     const size_t per = (size_t)m->S * m->D;
+    if (c->cross_impl == 1) {
+        WB_CHECK(convert_f32_bf16(m->stream, enc_out_dev, c->cross_enc, (size_t)c->B * per));
+        c->has_cross = true;
+        return WB_OK;
+    }
     for (int i = 0; i < c->B; i += m->enc_batch) {
         int nb = std::min(m->enc_batch, c->B - i);
         WB_CHECK(ensure_encoder_ws(m, nb));
@@ -415,6 +443,22 @@ int cache_set_encoder(Cache *c, const float *enc_out_dev) {
     }
     c->has_cross = true;
     return WB_OK;
+}
+
+template <typename Fn>
+static int timed_kernel(Model *m, cudaStream_t st, Fn launch) {
+    if (!m->profile_attn) return launch();
+    KernelTimer &t = m->cross_timer;
+    while ((int)t.ev.size() < t.used + 2) {
+        cudaEvent_t e;
+        WB_CUDA(cudaEventCreate(&e));
+        t.ev.push_back(e);
+    }
+    WB_CUDA(cudaEventRecord(t.ev[t.used], st));
+    int rc = launch();
+    WB_CUDA(cudaEventRecord(t.ev[t.used + 1], st));
+    t.used += 2;
+    return rc;
 }
 
 static int timed_cross_attention(Model *m, cudaStream_t st, const DecodeAttnArgs &a) {
@@ -447,7 +491,8 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     for (int l = 0; l < m->L; l++) {
         const LayerDev &d = m->dec[l];
         bf16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
-        bf16 *ck = c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off, *cv = ck + cross_seg;
+        bf16 *ck = c->cross_kv ? c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off : nullptr;
+        bf16 *cv = ck ? ck + cross_seg : nullptr;
         if (l > 0) WB_CHECK(ln_bf16(st, ln.x, d.ln1_g, d.ln1_b, B, D, ln.xn, nullptr));
         {  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
             GemmDesc g = plain_gemm(ln.xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, ln.q, D);
@@ -465,12 +510,21 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         WB_CHECK(gemm_run(st, plain_gemm(ln.attn, B, D, d.wo, D, d.bo, EPI_RESID_F32, ln.x, D), impl));
         // cross attention over the encoder positions (layers.mojo:463-488)
         WB_CHECK(ln_bf16(st, ln.x, d.ln2_g, d.ln2_b, B, D, ln.xn, nullptr));
-        WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, ln.q, D), impl));
-        a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;
-        a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
-        a.splits = ln.cross_splits, a.ws = ln.attn_ws;
-        WB_CHECK(timed_cross_attention(m, st, a));
-        WB_CHECK(gemm_run(st, plain_gemm(ln.attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, ln.x, D), impl));
+        if (c->cross_impl == 1) {
+            // absorbed form: q' = (Wk_h^T Wq_h) x + ..., attend over enc_out, out = (Wo Wv_h) ctx_h + ...
+            const int HD = m->H * D;
+            WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.wqk, HD, d.bqk, EPI_STORE_BF16, ln.qp, HD), impl));
+            const bf16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
+            WB_CHECK(timed_kernel(m, st, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
+            WB_CHECK(gemm_run(st, plain_gemm(ln.ctx, B, HD, d.wov, D, d.bov, EPI_RESID_F32, ln.x, D), impl));
+        } else {
+            WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, ln.q, D), impl));
+            a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;
+            a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
+            a.splits = ln.cross_splits, a.ws = ln.attn_ws;
+            WB_CHECK(timed_cross_attention(m, st, a));
+            WB_CHECK(gemm_run(st, plain_gemm(ln.attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, ln.x, D), impl));
+        }
         // MLP (layers.mojo:490-517)
         WB_CHECK(ln_bf16(st, ln.x, d.ln3_g, d.ln3_b, B, D, ln.xn, nullptr));
         WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, ln.h, m->F), impl));
@@ -572,7 +626,8 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
     {  // bound the cross K/V cache to about half of the free HBM
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        size_t per_chunk = (size_t)m->L * 2 * (m->S + T_cache) * m->D * sizeof(bf16);
+        size_t per_chunk = ((size_t)m->L * 2 * T_cache + (m->cross_impl == 1 ? (size_t)m->S : (size_t)m->L * 2 * m->S)) *
+                           m->D * sizeof(bf16);
         size_t cap = std::max<size_t>(1, (free_b / 2) / per_chunk);
         wave = (int)std::min<size_t>(wave, cap);
     }
@@ -580,7 +635,7 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
     int rc = WB_OK;
     for (int w0 = 0; w0 < n && rc == WB_OK; w0 += wave) {
         const int nb = std::min(wave, n - w0);
-        if (!c || c->B != nb || c->T != T_cache) {
+        if (!c || c->B != nb || c->T != T_cache || c->cross_impl != m->cross_impl) {
             if (c) cache_destroy(c);
             c = m->tr_cache = nullptr;
             rc = cache_create(m, nb, T_cache, false, m->decode_lanes, &c);

@@ -35,6 +35,8 @@ Layout make_layout(const wm_config &c);
 struct LayerDev {
     bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
     bf16 *cwq = nullptr, *cwo = nullptr;  // decoder cross-attention
+    bf16 *wqk = nullptr, *wov = nullptr;  // folded cross projections [H*D][D], [D][H*D] (absorbed form)
+    float *bqk = nullptr, *bov = nullptr;
     float *bqkv = nullptr;                // [3D]: q bias, zeros (k has no bias), v bias
     const float *bo, *b1, *b2, *cbq, *cbo;
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;  // attn_ln, cross_ln (dec), mlp_ln
@@ -54,7 +56,8 @@ struct Model {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
     int gemm_impl = 1, attn_impl = 1, use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048,
-        decode_lanes = 1;  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
+        decode_lanes = 1,  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
+        cross_impl = 1;    // 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (D <= 384)
     Layout lay;
     float *w32 = nullptr;
     bool loaded = false;
@@ -84,7 +87,7 @@ struct Model {
 struct Lane {
     int B = 0, b_off = 0;
     float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr;
-    bf16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr;
+    bf16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *qp = nullptr, *ctx = nullptr;
     int *part_idx = nullptr, *next = nullptr;
     int cross_splits = 1;
     GreedyState g;  // per-chunk arrays point into the cache-wide arrays at b_off; scalars are per lane
@@ -96,7 +99,9 @@ struct Cache {
     int host_len = 0;  // mirror of current_len for the step-wise API
     bool has_cross = false;
     bf16 *self_kv = nullptr;   // [L][2][B][T][D]
-    bf16 *cross_kv = nullptr;  // [L][2][B][S][D]
+    bf16 *cross_kv = nullptr;  // [L][2][B][S][D]   (cross_impl 0)
+    bf16 *cross_enc = nullptr; // [B][S][D]        (cross_impl 1: enc_out itself, shared by all layers)
+    int cross_impl = 0;
     int *tokens_out = nullptr, *out_len = nullptr, *cur_tok = nullptr, *done = nullptr, *scalars = nullptr;
     std::vector<Lane> lanes;
     std::vector<void *> owned;

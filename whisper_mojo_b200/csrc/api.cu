@@ -411,28 +411,31 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
 
 }  // extern "C"
 
-// Stage a host array on the device (grow-only buffers owned by the model), run `fn(dev_in, dev_out)`,
-// copy the result back.  The host pointers may be pageable or pinned; pinned makes the copies async DMA.
+// Grow-only device staging buffers owned by the model (host-pointer entry points).
+static bool stage_grow(void **p, size_t *cap, size_t bytes) {
+    if (*cap >= bytes) return true;
+    cudaFree(*p);
+    *p = nullptr, *cap = 0;
+    if (cudaMalloc(p, bytes) != cudaSuccess) {
+        set_error("staging allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return false;
+    }
+    *cap = bytes;
+    return true;
+}
+
+// Stage a host array on the device, run `fn(dev_in, dev_out)`, copy the result back.  The host pointers
+// may be pageable or pinned; pinned makes the copies async DMA.  With `upload == false` the input copy is
+// left to `fn` (transcribe pipelines it against the compute, model.cu).
 template <typename Tin, typename Tout, typename Fn>
-static int staged(Model *m, const Tin *in_host, size_t n_in, Tout *out_host, size_t n_out, Fn fn) {
-    auto grow = [&](void **p, size_t *cap, size_t bytes) {
-        if (*cap >= bytes) return true;
-        cudaFree(*p);
-        *p = nullptr, *cap = 0;
-        if (cudaMalloc(p, bytes) != cudaSuccess) {
-            set_error("staging allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
-            return false;
-        }
-        *cap = bytes;
-        return true;
-    };
-    if (!grow(&m->stage_in, &m->stage_in_cap, std::max<size_t>(n_in, 1) * sizeof(Tin)) ||
-        !grow(&m->stage_out, &m->stage_out_cap, std::max<size_t>(n_out, 1) * sizeof(Tout)))
+static int staged(Model *m, const Tin *in_host, size_t n_in, Tout *out_host, size_t n_out, Fn fn, bool upload = true) {
+    if (!stage_grow(&m->stage_in, &m->stage_in_cap, std::max<size_t>(n_in, 1) * sizeof(Tin)) ||
+        !stage_grow(&m->stage_out, &m->stage_out_cap, std::max<size_t>(n_out, 1) * sizeof(Tout)))
         return WB_ERR_CUDA;
     Tin *din = reinterpret_cast<Tin *>(m->stage_in);
     Tout *dout = reinterpret_cast<Tout *>(m->stage_out);
     int rc = WB_OK;
-    if (cudaMemcpyAsync(din, in_host, n_in * sizeof(Tin), cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
+    if (upload && cudaMemcpyAsync(din, in_host, n_in * sizeof(Tin), cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
         rc = WB_ERR_CUDA;
     if (rc == WB_OK) rc = fn(din, dout);
     if (rc == WB_OK &&
@@ -440,6 +443,7 @@ static int staged(Model *m, const Tin *in_host, size_t n_in, Tout *out_host, siz
         rc = WB_ERR_CUDA;
     if (rc == WB_OK && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = WB_ERR_CUDA;
     if (rc == WB_ERR_CUDA && g_err[0] == 0) set_error("CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != WB_OK && !upload) cudaStreamSynchronize(m->stream2);  // uploads still in flight read in_host
     return rc;
 }
 
@@ -535,8 +539,8 @@ static int transcribe_host(Model *m, const float *in_host, bool pcm, int n, int3
     // tokens and lengths share one staging buffer: [n*T_out tokens][n lengths]
     std::vector<int32_t> tmp((size_t)n * T_out + n);
     int rc = staged(m, in_host, n_in, tmp.data(), tmp.size(), [&](const float *i, int32_t *o) {
-        return model_transcribe(m, pcm ? nullptr : i, pcm ? i : nullptr, n, o, o + (size_t)n * T_out);
-    });
+        return model_transcribe(m, pcm ? nullptr : i, pcm ? i : nullptr, n, o, o + (size_t)n * T_out, in_host);
+    }, /*upload=*/false);
     if (rc == WB_OK) {
         memcpy(out_tokens_host, tmp.data(), (size_t)n * T_out * 4);
         memcpy(out_len_host, tmp.data() + (size_t)n * T_out, (size_t)n * 4);

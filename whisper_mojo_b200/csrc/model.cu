@@ -127,12 +127,15 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
 void model_destroy(Model *m) {
     if (!m) return;
     cudaStreamSynchronize(m->stream);
+    if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->tr_cache) cache_destroy(m->tr_cache);
     cudaFree(m->tr_mel);
     cudaFree(m->stage_in);
     cudaFree(m->stage_out);
     for (void *p : m->owned) cudaFree(p);
     for (cudaEvent_t e : m->cross_timer.ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->ev_plain) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->ev_timed) cudaEventDestroy(e);
     frontend_tables_destroy(&m->ft);
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -610,18 +613,36 @@ static int greedy_loop(Cache *c) {
     return WB_OK;
 }
 
+// Events used to pipeline / time the per-sub-batch work of one transcribe call (grow-only pool).
+static int event_pool(Model *m, size_t n_plain, size_t n_timed) {
+    while (m->ev_plain.size() < n_plain) {
+        cudaEvent_t e;
+        WB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        m->ev_plain.push_back(e);
+    }
+    while (m->ev_timed.size() < n_timed) {
+        cudaEvent_t e;
+        WB_CUDA(cudaEventCreate(&e));
+        m->ev_timed.push_back(e);
+    }
+    return WB_OK;
+}
+
+// `in_host` (optional): the input still lives in host memory and `mel_dev` / `pcm_dev` is an empty staging
+// buffer of the same size.  The upload is then cut into encoder sub-batches and issued on the copy stream,
+// and the frontend + encoder of sub-batch i wait only for their own slice, so the PCIe transfer of the
+// following slices runs under the compute of the earlier ones (pinned host memory makes the copies async).
 int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
-                     int32_t *out_len_dev) {
+                     int32_t *out_len_dev, const float *in_host) {
     WB_ARG(m->loaded, "transcribe before weights are loaded");
     WB_ARG(n > 0 && (mel_dev || pcm_dev) && out_tokens_dev && out_len_dev, "transcribe: bad arguments");
     cudaStream_t st = m->stream;
     const int T_out = 5 + m->cfg.max_iters;
     const int T_cache = std::min(m->T, (T_out + 7) & ~7);
-    cudaEvent_t ev[5];
-    for (auto &e : ev) WB_CUDA(cudaEventCreate(&e));
-    float acc[4] = {0, 0, 0, 0};
     m->cross_timer.used = 0;
     const size_t mel_per = (size_t)m->NM * m->n_frames;
+    const size_t in_per = mel_dev ? mel_per : (size_t)m->n_samples;
+    float *in_dev = const_cast<float *>(mel_dev ? mel_dev : pcm_dev);
     int wave = std::min(n, m->wave_max);
     {  // bound the cross K/V cache to about half of the free HBM
         size_t free_b = 0, total_b = 0;
@@ -631,9 +652,36 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
         size_t cap = std::max<size_t>(1, (free_b / 2) / per_chunk);
         wave = (int)std::min<size_t>(wave, cap);
     }
+    const int eb = m->enc_batch;
+    // sub-batches never straddle a wave: enumerate them once so the uploads can all be queued up front
+    std::vector<std::pair<int, int>> subs;  // (first chunk, count)
+    for (int w0 = 0; w0 < n; w0 += wave)
+        for (int i = w0; i < std::min(n, w0 + wave); i += eb) subs.push_back({i, std::min(eb, std::min(n, w0 + wave) - i)});
+    const size_t n_waves = (size_t)cdiv(n, wave);
+    WB_CHECK(event_pool(m, subs.size() + 1, 3 * subs.size() + 2 * n_waves));
+    if (in_host) {
+        // the staging buffer may still be read by work queued earlier on the compute stream
+        WB_CUDA(cudaEventRecord(m->ev_plain[subs.size()], st));
+        WB_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_plain[subs.size()], 0));
+        for (size_t k = 0; k < subs.size(); k++) {
+            const size_t off = (size_t)subs[k].first * in_per, cnt = (size_t)subs[k].second * in_per;
+            WB_CUDA(cudaMemcpyAsync(in_dev + off, in_host + off, cnt * 4, cudaMemcpyHostToDevice, m->stream2));
+            WB_CUDA(cudaEventRecord(m->ev_plain[k], m->stream2));
+        }
+    }
+    if (!mel_dev && m->tr_mel_cap < (size_t)std::min(eb, n) * mel_per) {  // log-mel of one sub-batch
+        cudaFree(m->tr_mel);
+        m->tr_mel = nullptr, m->tr_mel_cap = 0;
+        if (cudaMalloc((void **)&m->tr_mel, (size_t)eb * mel_per * 4) != cudaSuccess) {
+            set_error("transcribe: cannot allocate the log-mel buffer");
+            return WB_ERR_CUDA;
+        }
+        m->tr_mel_cap = (size_t)eb * mel_per;
+    }
     Cache *c = m->tr_cache;  // reused across calls while the wave size stays the same
     int rc = WB_OK;
-    for (int w0 = 0; w0 < n && rc == WB_OK; w0 += wave) {
+    size_t k = 0, wv = 0;
+    for (int w0 = 0; w0 < n && rc == WB_OK; w0 += wave, wv++) {
         const int nb = std::min(wave, n - w0);
         if (!c || c->B != nb || c->T != T_cache || c->cross_impl != m->cross_impl) {
             if (c) cache_destroy(c);
@@ -645,56 +693,52 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
             rc = cache_reset(c);
             if (rc != WB_OK) break;
         }
-        cudaEventRecord(ev[0], st);
-        const float *mel_w = mel_dev ? mel_dev + w0 * mel_per : nullptr;
-        if (!mel_dev) {  // frontend
-            if (m->tr_mel_cap < (size_t)wave * mel_per) {
-                cudaFree(m->tr_mel);
-                m->tr_mel = nullptr, m->tr_mel_cap = 0;
-                if (cudaMalloc((void **)&m->tr_mel, (size_t)wave * mel_per * 4) != cudaSuccess) {
-                    set_error("transcribe: cannot allocate the log-mel buffer");
-                    rc = WB_ERR_CUDA;
-                    break;
-                }
-                m->tr_mel_cap = (size_t)wave * mel_per;
-            }
-            rc = model_logmel(m, pcm_dev + (size_t)w0 * m->n_samples, nb, m->tr_mel);
-            if (rc != WB_OK) break;
-            mel_w = m->tr_mel;
+        for (int i = w0; i < w0 + nb && rc == WB_OK; i += eb, k++) {
+            const int ns = std::min(eb, w0 + nb - i);
+            if (in_host) WB_CUDA(cudaStreamWaitEvent(st, m->ev_plain[k], 0));
+            cudaEventRecord(m->ev_timed[3 * k], st);
+            const float *mel_s = mel_dev ? mel_dev + (size_t)i * mel_per : m->tr_mel;
+            if (!mel_dev) rc = model_logmel(m, pcm_dev + (size_t)i * m->n_samples, ns, m->tr_mel);
+            cudaEventRecord(m->ev_timed[3 * k + 1], st);
+            if (rc == WB_OK) rc = encode_batch(m, mel_s, ns, nullptr, c, i - w0);
+            cudaEventRecord(m->ev_timed[3 * k + 2], st);
         }
-        cudaEventRecord(ev[1], st);
-        rc = model_encode(m, mel_w, nb, nullptr, c, 0);
         if (rc != WB_OK) break;
-        cudaEventRecord(ev[2], st);
+        c->has_cross = true;
+        cudaEvent_t d0 = m->ev_timed[3 * subs.size() + 2 * wv], d1 = m->ev_timed[3 * subs.size() + 2 * wv + 1];
+        cudaEventRecord(d0, st);
         rc = greedy_loop(c);
         if (rc != WB_OK) break;
-        cudaEventRecord(ev[3], st);
+        cudaEventRecord(d1, st);
         cudaMemcpyAsync(out_tokens_dev + (size_t)w0 * T_out, c->tokens_out, (size_t)nb * T_out * 4,
                         cudaMemcpyDeviceToDevice, st);
         cudaMemcpyAsync(out_len_dev + w0, c->out_len, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st);
-        if (cudaStreamSynchronize(st) != cudaSuccess) {
+        if (cudaStreamSynchronize(st) != cudaSuccess) {  // the next wave reuses the cache
             set_error("transcribe: %s", cudaGetErrorString(cudaGetLastError()));
             rc = WB_ERR_CUDA;
             break;
         }
-        float ms;
-        for (int i = 0; i < 3; i++) {
-            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-            acc[i == 0 ? 0 : (i == 1 ? 1 : 3)] += ms;
-        }
     }
     if (rc == WB_OK) {
+        float acc[3] = {0, 0, 0}, ms = 0.f;
+        for (size_t i = 0; i < subs.size(); i++) {
+            if (cudaEventElapsedTime(&ms, m->ev_timed[3 * i], m->ev_timed[3 * i + 1]) == cudaSuccess) acc[0] += ms;
+            if (cudaEventElapsedTime(&ms, m->ev_timed[3 * i + 1], m->ev_timed[3 * i + 2]) == cudaSuccess) acc[1] += ms;
+        }
+        for (size_t i = 0; i < n_waves; i++)
+            if (cudaEventElapsedTime(&ms, m->ev_timed[3 * subs.size() + 2 * i], m->ev_timed[3 * subs.size() + 2 * i + 1]) ==
+                cudaSuccess)
+                acc[2] += ms;
         // cross-K/V projection time is part of encode_batch; report it inside [1] and leave [2] = 0
-        m->timing[0] = acc[0], m->timing[1] = acc[1], m->timing[2] = 0.f, m->timing[3] = acc[3];
-        m->timing[4] = acc[0] + acc[1] + acc[3];
+        m->timing[0] = acc[0], m->timing[1] = acc[1], m->timing[2] = 0.f, m->timing[3] = acc[2];
+        m->timing[4] = acc[0] + acc[1] + acc[2];
         KernelTimer &t = m->cross_timer;
         t.total_ms = 0.f, t.launches = 0;
         for (int i = 0; i + 1 < t.used; i += 2) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.total_ms += ms, t.launches++;
+            float ems = 0.f;
+            if (cudaEventElapsedTime(&ems, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.total_ms += ems, t.launches++;
         }
     }
-    for (auto &e : ev) cudaEventDestroy(e);
     return rc;
 }
 

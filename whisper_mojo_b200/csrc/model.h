@@ -52,7 +52,7 @@ struct KernelTimer {
 struct Model {
     wm_config cfg;
     int D, H, L, V, S, T, NM, F, n_frames, n_samples;
-    cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second decode lane
+    cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: host->device uploads, second decode lane
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
     int gemm_impl = 1, attn_impl = 1, use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048,
@@ -73,6 +73,7 @@ struct Model {
     float *e_x = nullptr;
     float timing[5] = {0, 0, 0, 0, 0};
     KernelTimer cross_timer;
+    std::vector<cudaEvent_t> ev_plain, ev_timed;  // per-sub-batch upload / phase-timing events of transcribe
     // transcribe workspace kept across calls (allocation of a 19 GB cache costs ~0.2 s per call otherwise)
     struct Cache *tr_cache = nullptr;
     float *tr_mel = nullptr;
@@ -120,7 +121,7 @@ int cache_reset(Cache *c);
 int cache_set_encoder(Cache *c, const float *enc_out_dev);
 int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits);
 int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
-                     int32_t *out_len_dev);
+                     int32_t *out_len_dev, const float *in_host = nullptr);
 int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_t *forced_host, int n_forced,
                          float *logits_host);
 int cache_step_api(Cache *c, const int32_t *tokens_host, int start_pos, float *logits_host, int32_t *next_host);

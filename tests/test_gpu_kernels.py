@@ -63,6 +63,40 @@ def test_gemm_conv_taps(cs, Cin, L, N, B):
         assert np.abs(out.reshape(B, Lo, N) - ref).max() <= 1e-4, impl
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 1152, 384), (700, 384, 1536), (129, 130, 192), (1, 1000, 128),
+                                   (2500, 1536, 384), (40000, 384, 384)])
+def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
+    """cta_group::2 kernel (impl 3 forces it): 256 x {128,192,256} pair tiles, ragged M / N, many tiles per pair."""
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+    b = rng.standard_normal(N, dtype=np.float32)
+    ref = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T + b
+    tol = 2e-5 * max(1.0, K / 64)
+    f32 = debug_gemm(3, A, W, b, 3)
+    assert np.abs(f32 - ref).max() <= tol
+    assert np.array_equal(f32, debug_gemm(2, A, W, b, 3))  # same k order as the single-CTA kernel: bit-identical
+    assert np.array_equal(debug_gemm(3, A, W, b, 0), bf16_round(f32))
+    g = torch.nn.functional.gelu(torch.from_numpy(ref), approximate="tanh").numpy()
+    assert np.abs(debug_gemm(3, A, W, b, 1) - g).max() <= 2e-2
+    x0 = rng.standard_normal((M, N), dtype=np.float32)
+    assert np.abs(debug_gemm(3, A, W, b, 2, out0=x0) - (x0 + ref)).max() <= tol
+
+
+@pytest.mark.parametrize("cs,Cin,L,N,B", [(1, 128, 300, 128, 2), (2, 128, 301, 256, 3), (2, 384, 3000, 384, 2), (1, 128, 3000, 384, 3)])
+def test_gemm_cta_pair_conv_taps(cs, Cin, L, N, B):
+    A = rng.standard_normal((B, L, Cin), dtype=np.float32)
+    W = rng.standard_normal((N, 3 * Cin), dtype=np.float32) / np.sqrt(3 * Cin)
+    Lo = (L + 2 - 3) // cs + 1
+    Ab, Wb = bf16_round(A).astype(np.float64), bf16_round(W).astype(np.float64)
+    ref = np.zeros((B, Lo, N))
+    for t in range(3):
+        rows = np.arange(Lo) * cs + t - 1
+        ok = (rows >= 0) & (rows < L)
+        ref[:, ok] += Ab[:, rows[ok]] @ Wb[:, t * Cin:(t + 1) * Cin].T
+    out = debug_gemm(3, A, W, None, 3, batches=B, taps=3, conv_stride=cs, pad=1, rows_per_batch=Lo)
+    assert np.abs(out.reshape(B, Lo, N) - ref).max() <= 1e-4
+
+
 @pytest.mark.parametrize("B,H,ln,splits", [(3, 6, 1500, 1), (3, 6, 1500, 11), (2, 2, 96, 1), (2, 12, 200, 1), (1, 6, 1, 1),
                                            (2, 6, 2, 1), (2, 6, 3, 1), (2, 6, 17, 1), (2, 6, 19, 1), (1, 6, 1500, 7)])
 def test_decode_attention(B, H, ln, splits):

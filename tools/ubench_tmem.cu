@@ -1,0 +1,98 @@
+// ubench_tmem.cu -- microbenchmarks that size the softmax / epilogue warps of the tcgen05 kernels:
+//   (1) tcgen05.ld 32x32b.x32 throughput with 1..4 warps of a CTA (one per TMEM lane quarter) and
+//       with 1 or 2 CTAs per SM,
+//   (2) MUFU.EX2 throughput per SM.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ubench_tmem tools/ubench_tmem.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../whisper_mojo_b200/csrc/sm100.cuh"
+
+using namespace wb;
+
+__global__ void __launch_bounds__(128) ldtm_kernel(int iters, int active_warps, long long *out, float *sink) {
+    __shared__ uint32_t holder;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        ptx::tmem_alloc(&holder, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t base = holder;
+    float acc = 0.f;
+    long long t0 = 0, t1 = 0;
+    if (warp < active_warps) {
+        const uint32_t addr = base + ((uint32_t)(warp * 32) << 16);
+        t0 = clock64();
+        for (int i = 0; i < iters; i++) {
+            uint32_t v[128];
+            ptx::tmem_ld_32x32b_x32(addr, v);
+            ptx::tmem_ld_32x32b_x32(addr + 32, v + 32);
+            ptx::tmem_ld_32x32b_x32(addr + 64, v + 64);
+            ptx::tmem_ld_32x32b_x32(addr + 96, v + 96);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 128; t += 16) acc += __uint_as_float(v[t]);
+        }
+        t1 = clock64();
+    }
+    __syncthreads();
+    if (lane == 0 && warp < active_warps) out[blockIdx.x * 4 + warp] = t1 - t0;
+    if (acc == 12345.678f) sink[0] = acc;
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(base, 256);
+}
+
+__global__ void __launch_bounds__(512) mufu_kernel(int iters, long long *out, float *sink) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = -1e-3f * (threadIdx.x + i);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = ptx::ex2(x[i]) - 1.0f;
+    }
+    long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += x[i];
+    if (s == 12345.678f) sink[0] = s;
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+}
+
+int main() {
+    long long *out;
+    float *sink;
+    cudaMalloc(&out, 4096 * sizeof(long long));
+    cudaMalloc(&sink, 16);
+    long long h[4096];
+    const int iters = 2000;
+    for (int ctas_per_sm = 1; ctas_per_sm <= 2; ctas_per_sm++)
+        for (int w = 1; w <= 4; w++) {
+            const int grid = 148 * ctas_per_sm;
+            ldtm_kernel<<<grid, 128>>>(iters, w, out, sink);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+                printf("ldtm error %s\n", cudaGetErrorString(e));
+                return 1;
+            }
+            cudaMemcpy(h, out, grid * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+            double clk = (double)h[0] / iters;
+            // bytes per warp per iteration: 32 lanes x 128 columns x 4 B = 16 KiB
+            printf("ldtm: %d CTA/SM, %d warps/CTA: %.1f clk per 16 KiB/warp -> %.1f B/clk/warp, %.1f B/clk/SM\n",
+                   ctas_per_sm, w, clk, 16384.0 / clk, 16384.0 * w * ctas_per_sm / clk);
+        }
+    for (int threads = 128; threads <= 512; threads *= 2) {
+        mufu_kernel<<<148, threads>>>(iters, out, sink);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, out, sizeof(long long), cudaMemcpyDeviceToHost);
+        double clk = (double)h[0] / iters;
+        printf("mufu.ex2 (+fadd): %d threads/SM: %.1f clk per 16 ex2/thread -> %.2f ex2/clk/SM\n", threads, clk,
+               16.0 * threads / clk);
+    }
+    return 0;
+}

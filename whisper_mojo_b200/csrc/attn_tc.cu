@@ -11,9 +11,11 @@
 //                          O += P_j V_j (UMMA 128x64x16, P K-major from smem, V MN-major from smem)
 //                          into TMEM cols [128,192); S_{j+1} is issued before PV_j so it overlaps
 //                          the softmax of block j
-//   warps 0-3 softmax    : thread = query row; two passes over S in TMEM (max, then exp2 -> bf16 P
-//                          into 128B-swizzled smem), online-softmax rescale of O through
-//                          tcgen05.ld/st only when a row maximum moved
+//   warps 0-3 softmax    : thread = query row; the 128 scores of the block are pulled into registers
+//                          with one TMEM read (S is released to the MMA warp right away), then max,
+//                          ex2.approx -> bf16 P into 128B-swizzled smem; the online-softmax shift is
+//                          lazy (moves only when the maximum grows by > 2^8), so the O rescale through
+//                          tcgen05.ld/st is rare.  Bound: MUFU.EX2, 16/clk/SM = 1024 clk per 128x128 block
 //
 // 96 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's MMAs run
 // under the other's exponentials.  Output: O / l in bf16, one 128-byte row segment per thread.
@@ -132,60 +134,69 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
         const int row = warp * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-        float m_run = -INFINITY, l_run = 0.f;
+        // Lazy rescale: the running shift m_use only moves when a block's maximum exceeds it by more than
+        // TAU (in score units: 2^8 after scaling), so p <= 256 and the O/l rescale is rare after block 0.
+        const float TAU = 8.0f / c;
+        float m_use = -INFINITY, l_run = 0.f;
         uint8_t *p_row = sP + row * 128;
         const int sw = row & 7;
         for (int j = 0; j < nblk; j++) {
             const int kvalid = min(128, P.S - j * 128);  // keys of this block inside the chunk
             ptx::mbar_wait(s_full, j & 1);
             ptx::tc_fence_after();
-            // pass 1: row maximum
-            float m_blk = -INFINITY;
-#pragma unroll 1
-            for (int cc = 0; cc < 4; cc++) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(tS + lane_addr + cc * 32, v);
-                ptx::tmem_ld_wait();
+            // the whole 128-key score row into registers with one wait, then hand S back to the MMA warp
+            uint32_t v[128];
+            ptx::tmem_ld_32x32b_x32(tS + lane_addr, v);
+            ptx::tmem_ld_32x32b_x32(tS + lane_addr + 32, v + 32);
+            ptx::tmem_ld_32x32b_x32(tS + lane_addr + 64, v + 64);
+            ptx::tmem_ld_32x32b_x32(tS + lane_addr + 96, v + 96);
+            ptx::tmem_ld_wait();
 #pragma unroll
-                for (int t = 0; t < 32; t++)
-                    if (cc * 32 + t < kvalid) m_blk = fmaxf(m_blk, __uint_as_float(v[t]));
-            }
-            const float m_new = fmaxf(m_run, m_blk);
-            const float alpha = exp2f((m_run - m_new) * c);  // 0 on the first block (m_run = -inf)
-            const float mc = m_new * c;
-            if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O holds blocks < j
-            // pass 2: p = exp2(s*c - m*c) -> bf16 -> swizzled smem (K-major A operand), row sum in fp32
-            float l_blk = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < 4; cc++) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(tS + lane_addr + cc * 32, v);
-                ptx::tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    float p0 = (cc * 32 + t < kvalid) ? exp2f(__uint_as_float(v[t]) * c - mc) : 0.f;
-                    float p1 = (cc * 32 + t + 1 < kvalid) ? exp2f(__uint_as_float(v[t + 1]) * c - mc) : 0.f;
-                    l_blk += p0 + p1;
-                    pk[t >> 1] = pack_bf16x2(p0, p1);
-                }
-                // 32 keys = 4 chunks of 16 B; key index cc*32 .. -> sub-tile cc>>1, chunk (cc&1)*4 + i
-                uint8_t *dst = p_row + (cc >> 1) * TILE_BYTES;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int chunk = (cc & 1) * 4 + i;
-                    *reinterpret_cast<uint4 *>(dst + ((chunk ^ sw) << 4)) =
-                        make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                }
-            }
-            // S_j is fully consumed: let the MMA warp overwrite it with S_{j+1}
+            for (int t = 0; t < 128; t++) asm volatile("" : "+r"(v[t]));  // no use of v[] may move above the wait
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(s_empty);
-            l_run = l_run * alpha + l_blk;
-            m_run = m_new;
-            // rescale the running output when some row of this warp moved its maximum
+            if (lane == 0) ptx::mbar_arrive(s_empty);  // S_{j+1} = Q K_{j+1}^T runs under this block's exponentials
+            if (kvalid < 128) {
+#pragma unroll
+                for (int t = 0; t < 128; t++)
+                    if (t >= kvalid) v[t] = 0xff800000u;  // -inf: exp2 -> 0, never the maximum
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < 128; t += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[t])), mx1 = fmaxf(mx1, __uint_as_float(v[t + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(v[t + 2])), mx3 = fmaxf(mx3, __uint_as_float(v[t + 3]));
+            }
+            const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            float alpha = 1.0f;
+            if (j == 0) {
+                m_use = m_blk;
+            } else if (m_blk > m_use + TAU) {
+                alpha = ptx::ex2((m_use - m_blk) * c);
+                m_use = m_blk;
+            }
+            const float nmc = -m_use * c;
+            // p = exp2(s*c - m*c) -> bf16 pairs, in place over the score registers; row sum in fp32
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 128; t += 2) {
+                const float p0 = ptx::ex2(fmaf(__uint_as_float(v[t]), c, nmc));
+                const float p1 = ptx::ex2(fmaf(__uint_as_float(v[t + 1]), c, nmc));
+                l0 += p0, l1 += p1;
+                v[t >> 1] = pack_bf16x2(p0, p1);
+            }
+            l_run = l_run * alpha + (l0 + l1);
+            if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O holds blocks < j
+            // P -> swizzled smem (K-major A operand): 128 keys = 2 sub-tiles x 8 chunks of 16 B
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint8_t *dst = p_row + (i >> 3) * TILE_BYTES;
+                *reinterpret_cast<uint4 *>(dst + (((i & 7) ^ sw) << 4)) =
+                    make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            // rescale the running output when some row of this warp moved its shift
             if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+                ptx::tc_fence_after();
 #pragma unroll 1
                 for (int cc = 0; cc < 2; cc++) {
                     uint32_t o[32];

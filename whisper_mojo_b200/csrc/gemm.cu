@@ -13,6 +13,7 @@
 
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -24,7 +25,7 @@ static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
 static constexpr int A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
 static constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 static constexpr int PART_PER_TILE = 2;  // argmax partials per 128-column tile (one per epilogue column half)
-static constexpr int TC_SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+static constexpr int TC_SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 8 * 128 * 4;
 
 // Device-visible parameters (shared by both implementations).
 struct GemmDev {
@@ -150,32 +151,92 @@ __global__ void __launch_bounds__(256) gemm_ref_kernel(const GemmDev p) {
 // Tensor-core kernel
 // ---------------------------------------------------------------------------------------------
 
-// Epilogue for one thread = one output row, 32 consecutive columns starting at n (n % 32 == 0).
+// Epilogue for one thread = one output row, 32 consecutive columns starting at n (n % 32 == 0), in two
+// steps so that no global-memory latency sits between the TMEM read and the stores: `epi_prefetch` issues
+// every load the chunk needs (bias, and the old residual / positional values) as independent 128-bit
+// loads -- the kernels call it for chunk c+1 before they finish chunk c -- and `epi_finish` adds, applies
+// the activation and stores.  The bias slice of the tile is staged in shared memory once per tile by
+// `stage_bias` (one coalesced load per warp instead of 8 serial L2-latency loads per chunk).
+// Warp-cooperative: sbias[0, ncols) = bias[n0 .. n0+ncols) (zero past N or without a bias); ncols <= 128.
+__device__ __forceinline__ void stage_bias(const GemmDev &p, int n0, int ncols, float *sbias, int lane) {
+    __syncwarp();  // every lane is done with the previous tile's values
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int j = lane + 32 * t;
+        if (j < ncols) sbias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+    }
+    __syncwarp();
+}
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_row32(const GemmDev &p, int b, int m, int n, const uint32_t *vraw,
-                                               float &best, int &best_idx) {
+struct EpiChunk {
+    float extra[32];  // EPI_RESID_F32: the values being added to; EPI_GELU_POS_F32: positional embedding
+    void *dst;
+    bool active, full, vec;
+};
+
+template <int EPI>
+__device__ __forceinline__ void epi_prefetch(const GemmDev &p, int b, int m, int n, EpiChunk<EPI> &e) {
+    e.active = (m < p.rows_per_batch && n < p.N);
+    e.dst = nullptr, e.full = e.vec = false;
+    if (!e.active) return;
+    e.full = (n + 32 <= p.N);
+    if (EPI == EPI_ARGMAX) return;
     const long long grow = (long long)b * p.rows_per_batch + m;
+    int seg;
+    long long off;
+    out_location(p, grow, n, seg, off);
+    if (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16) {
+        e.dst = reinterpret_cast<__nv_bfloat16 *>(p.out[seg]) + off;
+        e.vec = e.full && ((reinterpret_cast<uintptr_t>(e.dst) & 15) == 0);
+        return;
+    }
+    float *dst = reinterpret_cast<float *>(p.out[seg]) + off;
+    e.dst = dst;
+    e.vec = e.full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (EPI == EPI_RESID_F32) {
+        if (e.vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 o = *reinterpret_cast<const float4 *>(dst + j);
+                e.extra[j] = o.x, e.extra[j + 1] = o.y, e.extra[j + 2] = o.z, e.extra[j + 3] = o.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) e.extra[j] = (n + j < p.N) ? dst[j] : 0.f;
+        }
+    } else if (EPI == EPI_GELU_POS_F32) {
+        const float *pos = p.pos + (long long)m * p.N + n;
+        if (e.full && ((reinterpret_cast<uintptr_t>(pos) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 o = __ldg(reinterpret_cast<const float4 *>(pos + j));
+                e.extra[j] = o.x, e.extra[j + 1] = o.y, e.extra[j + 2] = o.z, e.extra[j + 3] = o.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) e.extra[j] = (n + j < p.N) ? __ldg(pos + j) : 0.f;
+        }
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_finish(const GemmDev &p, int b, int m, int n, const uint32_t *vraw,
+                                           const EpiChunk<EPI> &e, const float *sbias, float &best, int &best_idx) {
+    if (!e.active) return;
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(vraw[j]);
-    if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            if (n + j + 3 < p.N) {
-                float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + n + j));
-                v[j] += bv.x, v[j + 1] += bv.y, v[j + 2] += bv.z, v[j + 3] += bv.w;
-            } else {
-#pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (n + j + t < p.N) v[j + t] += __ldg(p.bias + n + j + t);
-            }
-        }
+    for (int j = 0; j < 32; j += 4) {  // sbias: this chunk's 32 bias values in shared memory (broadcast reads)
+        const float4 bv = *reinterpret_cast<const float4 *>(sbias + j);
+        v[j] = __uint_as_float(vraw[j]) + bv.x, v[j + 1] = __uint_as_float(vraw[j + 1]) + bv.y;
+        v[j + 2] = __uint_as_float(vraw[j + 2]) + bv.z, v[j + 3] = __uint_as_float(vraw[j + 3]) + bv.w;
     }
     if (EPI == EPI_ARGMAX) {
 #pragma unroll
         for (int j = 0; j < 32; j++)
             if (n + j < p.N && v[j] > best) best = v[j], best_idx = n + j;
         if (p.logits) {
+            const long long grow = (long long)b * p.rows_per_batch + m;
             float *dst = p.logits + grow * p.N + n;
 #pragma unroll
             for (int j = 0; j < 32; j++)
@@ -183,17 +244,13 @@ __device__ __forceinline__ void epilogue_row32(const GemmDev &p, int b, int m, i
         }
         return;
     }
-    const bool full = (n + 32 <= p.N);
-    int seg;
-    long long off;
-    out_location(p, grow, n, seg, off);
     if (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16) {
         if (EPI == EPI_GELU_BF16) {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = gelu_fast(v[j]);
         }
-        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out[seg]) + off;
-        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(e.dst);
+        if (e.vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 uint4 u;
@@ -208,34 +265,21 @@ __device__ __forceinline__ void epilogue_row32(const GemmDev &p, int b, int m, i
             for (int j = 0; j < 32; j++)
                 if (n + j < p.N) dst[j] = __float2bfloat16(v[j]);
         }
+        return;
+    }
+    float *dst = reinterpret_cast<float *>(e.dst);
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if (EPI == EPI_RESID_F32) v[j] = e.extra[j] + v[j];
+        else if (EPI == EPI_GELU_POS_F32) v[j] = gelu_ref(v[j]) + e.extra[j];
+    }
+    if (e.vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
-        float *dst = reinterpret_cast<float *>(p.out[seg]) + off;
-        const float *pos = (EPI == EPI_GELU_POS_F32) ? p.pos + (long long)m * p.N + n : nullptr;
-        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                if (EPI == EPI_RESID_F32) {
-                    o = *reinterpret_cast<const float4 *>(dst + j);
-                    o.x += v[j], o.y += v[j + 1], o.z += v[j + 2], o.w += v[j + 3];
-                } else if (EPI == EPI_GELU_POS_F32) {
-                    float4 pv = __ldg(reinterpret_cast<const float4 *>(pos + j));
-                    o.x = gelu_ref(v[j]) + pv.x, o.y = gelu_ref(v[j + 1]) + pv.y;
-                    o.z = gelu_ref(v[j + 2]) + pv.z, o.w = gelu_ref(v[j + 3]) + pv.w;
-                } else {
-                    o.x = v[j], o.y = v[j + 1], o.z = v[j + 2], o.w = v[j + 3];
-                }
-                *reinterpret_cast<float4 *>(dst + j) = o;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; j++)
-                if (n + j < p.N) {
-                    if (EPI == EPI_RESID_F32) dst[j] += v[j];
-                    else if (EPI == EPI_GELU_POS_F32) dst[j] = gelu_ref(v[j]) + pos[j];
-                    else dst[j] = v[j];
-                }
-        }
+        for (int j = 0; j < 32; j++)
+            if (n + j < p.N) dst[j] = v[j];
     }
 }
 
@@ -251,6 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES;
     uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + 2;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    float *bias_smem = reinterpret_cast<float *>(tiles + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256);  // [8][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.batches * p.tiles_m_per_batch * p.tiles_n;
@@ -326,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     } else {
         // ===== epilogue warps: TMEM lanes 32*(warp%4) .. +31, columns 64*half .. +63 =====
         const int q = warp & 3, half = (warp - 2) >> 2;
+        float *sbias = bias_smem + (warp - 2) * 128;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int acc = it & 1;
@@ -337,27 +383,190 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             ptx::tc_fence_after();
             float best = -INFINITY;
             int best_idx = 0x7fffffff;
-#pragma unroll 1
-            for (int c = half * 2; c < half * 2 + 2; c++) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-                ptx::tmem_ld_wait();
-                const int n = nt * BN + c * 32;
-                if (m < p.rows_per_batch && n < p.N) epilogue_row32<EPI>(p, b, m, n, v, best, best_idx);
-            }
+            const int n_first = nt * BN + half * 64;
+            EpiChunk<EPI> e0, e1;
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * 64;
+            ptx::tmem_ld_32x32b_x32(taddr, v0);
+            ptx::tmem_ld_32x32b_x32(taddr + 32, v1);
+            epi_prefetch<EPI>(p, b, m, n_first, e0);
+            epi_prefetch<EPI>(p, b, m, n_first + 32, e1);
+            stage_bias(p, n_first, 64, sbias, lane);
+            ptx::tmem_ld_wait();
+            // the accumulator is in registers: hand the TMEM buffer back before the stores
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_relaxed(&tmem_empty[acc]);
+            epi_finish<EPI>(p, b, m, n_first, v0, e0, sbias, best, best_idx);
+            epi_finish<EPI>(p, b, m, n_first + 32, v1, e1, sbias + 32, best, best_idx);
             if (EPI == EPI_ARGMAX && m < p.rows_per_batch) {
                 long long grow = (long long)b * p.rows_per_batch + m;
                 p.part_val[(grow * p.tiles_n + nt) * PART_PER_TILE + half] = best;
                 p.part_idx[(grow * p.tiles_n + nt) * PART_PER_TILE + half] = best_idx;
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair tensor-core kernel (cta_group::2).  The single-CTA kernel above re-reads 192 KB of operands
+// from L2 for every 128x128x384 tile, ~3x what the L2->SM fabric delivers at tensor-pipe speed, so the
+// large encoder GEMMs are L2-bound.  Here two CTAs on one TPC compute a 256 x BN2 tile with one UMMA
+// (M = 256): each CTA stages its own 128 rows of A and only HALF of the B tile (BN2/2 weight rows), the
+// tensor cores read the other half from the peer's shared memory -> half the operand traffic per flop.
+//   * both producers (one per CTA) feed the same ring position; their TMA loads complete on the LEADER's
+//     "full" barrier, the leader's MMA thread issues for the pair and its tcgen05.commit multicasts the
+//     "empty" / "accumulator full" arrivals to both CTAs;
+//   * each CTA's eight epilogue warps drain their own TMEM (128 lanes x BN2 columns) and arrive on the
+//     leader's "accumulator empty" barrier (remote arrive for the peer).
+// ---------------------------------------------------------------------------------------------
+static constexpr int PAIR_STAGES = 6, PAIR_STAGE_BYTES = 32768;  // A 16 KB + B up to 16 KB per CTA
+static constexpr int PAIR_SMEM_BYTES = 1024 + PAIR_STAGES * PAIR_STAGE_BYTES + 256 + 8 * 128 * 4;
+
+struct GemmPairParams {
+    CUtensorMap a_map[3];
+    CUtensorMap b_map;  // box {64, BN2/2}
+    GemmDev d;
+    int pair_tiles_m_per_batch, pair_tiles_n;
+};
+
+template <int EPI, int BN2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    gemm_pair_kernel(const __grid_constant__ GemmPairParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const GemmDev &p = P.d;
+    constexpr int B_ROWS = BN2 / 2, B_BYTES = B_ROWS * BK * 2;
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + PAIR_STAGES * PAIR_STAGE_BYTES);
+    uint64_t *full_bar = bars, *empty_bar = bars + PAIR_STAGES;
+    uint64_t *tmem_full = bars + 2 * PAIR_STAGES, *tmem_empty = bars + 2 * PAIR_STAGES + 2;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * PAIR_STAGES + 4);
+    float *bias_smem = reinterpret_cast<float *>(tiles + PAIR_STAGES * PAIR_STAGE_BYTES + 256);  // [8][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int total_tiles = p.batches * P.pair_tiles_m_per_batch * P.pair_tiles_n;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int t = 0; t < p.taps; t++) ptx::prefetch_tmap(&P.a_map[t]);
+        ptx::prefetch_tmap(&P.b_map);
+        for (int s = 0; s < PAIR_STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);   // used on the leader only
+            ptx::mbar_init(&empty_bar[s], 1);  // one multicast commit per use
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], 16);  // leader only: 8 epilogue warps of each CTA
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_pair(tmem_holder, 512);
+        ptx::tmem_relinquish_pair();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===== TMA producer (one per CTA) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair_id; tile < total_tiles; tile += n_pairs) {
+                const int nt = tile % P.pair_tiles_n, mt = tile / P.pair_tiles_n;
+                const int b = mt / P.pair_tiles_m_per_batch;
+                const int m0 = (mt % P.pair_tiles_m_per_batch) * 256 + (int)rank * BM;
+                const int n0 = nt * BN2 + (int)rank * B_ROWS;
+                for (int kb = 0; kb < p.num_kb; kb++) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_BYTES));
+                    const uint32_t bar = ptx::mapa_u32(&full_bar[stage], 0);
+                    uint8_t *sa = tiles + stage * PAIR_STAGE_BYTES, *sb = sa + A_STAGE_BYTES;
+                    const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * BK;
+                    ptx::tma_load_3d_pair(sa, &P.a_map[tap], bar, c0, m0 + p.a_row_off[tap], b);
+                    ptx::tma_load_2d_pair(sb, &P.b_map, bar, kb * BK, n0);
+                    if (++stage == PAIR_STAGES) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN2, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair_id; tile < total_tiles; tile += n_pairs, it++) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN2;
+                for (int kb = 0; kb < p.num_kb; kb++) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    uint8_t *sa = tiles + stage * PAIR_STAGE_BYTES, *sb = sa + A_STAGE_BYTES;
+                    const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sa), 1, 64);
+                    const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sb), 1, 64);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        ptx::mma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    ptx::mma_commit_pair(&empty_bar[stage], 3);
+                    if (++stage == PAIR_STAGES) stage = 0, phase ^= 1;
+                }
+                ptx::mma_commit_pair(&tmem_full[acc], 3);
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lanes 32*(warp%4) .. +31, columns [half*BN2/2, +BN2/2) =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        constexpr int CH = BN2 / 64;  // 32-column chunks per half
+        float *sbias = bias_smem + (warp - 2) * 128;
+        int it = 0;
+        for (int tile = pair_id; tile < total_tiles; tile += n_pairs, it++) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int nt = tile % P.pair_tiles_n, mt = tile / P.pair_tiles_n;
+            const int b = mt / P.pair_tiles_m_per_batch;
+            const int m = (mt % P.pair_tiles_m_per_batch) * 256 + (int)rank * BM + q * 32 + lane;
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            float best = -INFINITY;
+            int best_idx = 0x7fffffff;
+            const int n_first = nt * BN2 + half * (BN2 / 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2 + half * (BN2 / 2);
+            // software pipeline over the CH chunks: TMEM read of chunk c and every global load of chunk c+1
+            // are in flight while chunk c-1 is converted and stored
+            EpiChunk<EPI> e[2];
+            uint32_t v[2][32];
+            ptx::tmem_ld_32x32b_x32(taddr, v[0]);
+            epi_prefetch<EPI>(p, b, m, n_first, e[0]);
+            stage_bias(p, n_first, BN2 / 2, sbias, lane);
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                ptx::tmem_ld_wait();  // chunk c is in v[c & 1]
+                if (c + 1 < CH) {
+                    ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    epi_prefetch<EPI>(p, b, m, n_first + (c + 1) * 32, e[(c + 1) & 1]);
+                } else {
+                    // the whole accumulator slice has left TMEM: hand the buffer back before the last stores
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster_relaxed(ptx::mapa_u32(&tmem_empty[acc], 0));
+                }
+                epi_finish<EPI>(p, b, m, n_first + c * 32, v[c & 1], e[c & 1], sbias + c * 32, best, best_idx);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // the peer may still signal this CTA's barriers / read its shared memory
+    if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -419,6 +628,37 @@ static int launch_tc(cudaStream_t st, const GemmTcParams &P, int grid) {
     return WB_OK;
 }
 
+template <int EPI, int BN2>
+static int launch_pair(cudaStream_t st, const GemmPairParams &P, int grid) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        WB_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     PAIR_SMEM_BYTES));
+        attr_set = true;
+    }
+    gemm_pair_kernel<EPI, BN2><<<grid, TC_THREADS, PAIR_SMEM_BYTES, st>>>(P);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+template <int EPI>
+static int launch_pair_bn(cudaStream_t st, const GemmPairParams &P, int grid, int bn2) {
+    switch (bn2) {
+        case 256: return launch_pair<EPI, 256>(st, P, grid);
+        case 192: return launch_pair<EPI, 192>(st, P, grid);
+        default: return launch_pair<EPI, 128>(st, P, grid);
+    }
+}
+
+// Pair-tile width: the widest of 256 / 192 / 128 that wastes the fewest padded columns.
+static int pick_pair_bn(int N) {
+    int best = 128, best_cols = cdiv(N, 128) * 128;
+    for (int bn : {192, 256}) {
+        int cols = cdiv(N, bn) * bn;
+        if (cols <= best_cols) best = bn, best_cols = cols;
+    }
+    return best;
+}
+
 int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
     WB_ARG(d.A && d.W && d.N > 0 && d.Cin > 0 && d.taps >= 1 && d.taps <= 3, "gemm: bad operands");
     if (d.batches <= 0 || d.rows_per_batch <= 0) return WB_OK;
@@ -453,8 +693,9 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
     p.Cin = d.Cin;
     p.W = d.W;
     WB_ARG(d.epi == EPI_ARGMAX || d.out[0], "gemm: missing output");
-    WB_ARG(d.epi != EPI_ARGMAX || (d.logits || impl == GEMM_IMPL_TC), "gemm: reference argmax needs a logits buffer");
-    WB_ARG(p.seg_cols == d.N || p.seg_cols % BN == 0, "gemm: seg_cols must be a multiple of 128");
+    WB_ARG(d.epi != EPI_ARGMAX || (d.logits || impl != GEMM_IMPL_REF), "gemm: reference argmax needs a logits buffer");
+    WB_ARG(p.seg_cols == d.N || p.seg_cols % 32 == 0, "gemm: seg_cols must be a multiple of 32");
+    WB_ARG(impl >= GEMM_IMPL_REF && impl <= GEMM_IMPL_TC_PAIR, "gemm: unknown implementation %d", impl);
 
     if (impl == GEMM_IMPL_REF) {
         dim3 grid(cdiv(d.N, 64), d.batches * cdiv(d.rows_per_batch, 64));
@@ -481,12 +722,36 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
                                 3));
     }
     for (int t = d.taps; t < 3; t++) P.a_map[t] = P.a_map[0], p.a_row_off[t] = 0;
-    WB_CHECK(make_tmap_bf16(&P.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, BN, 2));
-
-    int total_tiles = p.batches * p.tiles_m_per_batch * p.tiles_n;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    // CTA-pair kernel for the large GEMMs (encoder, cross-K/V): at least one full wave of 256-row pair tiles.
+    const int pair_tiles_m = cdiv(d.rows_per_batch, 256);
+    const bool pair_ok = d.epi != EPI_ARGMAX;
+    const bool want_pair = impl == GEMM_IMPL_TC_PAIR ||
+                           (impl == GEMM_IMPL_TC && (int64_t)d.batches * pair_tiles_m * cdiv(d.N, 256) >= sms / 2);
+    if (pair_ok && want_pair) {
+        GemmPairParams Q;
+        const int bn2 = pick_pair_bn(d.N);  // output routing is per 32-column chunk, so any tile width works
+        for (int t = 0; t < 3; t++) Q.a_map[t] = P.a_map[t];
+        WB_CHECK(make_tmap_bf16(&Q.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, bn2 / 2, 2));
+        Q.d = p;
+        Q.pair_tiles_m_per_batch = pair_tiles_m;
+        Q.pair_tiles_n = cdiv(d.N, bn2);
+        const int total = d.batches * pair_tiles_m * Q.pair_tiles_n;
+        const int grid = 2 * std::min(total, sms / 2);
+        switch (d.epi) {
+            case EPI_STORE_BF16: return launch_pair_bn<EPI_STORE_BF16>(st, Q, grid, bn2);
+            case EPI_GELU_BF16: return launch_pair_bn<EPI_GELU_BF16>(st, Q, grid, bn2);
+            case EPI_RESID_F32: return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
+            case EPI_STORE_F32: return launch_pair_bn<EPI_STORE_F32>(st, Q, grid, bn2);
+            case EPI_GELU_POS_F32: return launch_pair_bn<EPI_GELU_POS_F32>(st, Q, grid, bn2);
+        }
+    }
+    WB_CHECK(make_tmap_bf16(&P.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, BN, 2));
+
+    int total_tiles = p.batches * p.tiles_m_per_batch * p.tiles_n;
     int grid = total_tiles < sms ? total_tiles : sms;
     switch (d.epi) {
         case EPI_STORE_BF16: return launch_tc<EPI_STORE_BF16>(st, P, grid);

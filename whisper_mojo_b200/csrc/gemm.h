@@ -21,7 +21,9 @@ enum GemmEpi {
     EPI_GELU_POS_F32 = 5,  // out_f32 = gelu(acc + bias) + pos[row_in_batch][n]   (conv2 + positional add)
 };
 
-enum GemmImpl { GEMM_IMPL_REF = 0, GEMM_IMPL_TC = 1 };
+// REF: CUDA-core bring-up kernel.  TC: tcgen05 kernels, CTA-pair (cta_group::2) variant for the large GEMMs and the
+// single-CTA one otherwise.  TC_SINGLE / TC_PAIR force one variant (tests, A/B measurements).
+enum GemmImpl { GEMM_IMPL_REF = 0, GEMM_IMPL_TC = 1, GEMM_IMPL_TC_SINGLE = 2, GEMM_IMPL_TC_PAIR = 3 };
 
 // Host-side description of one GEMM.
 //   A(b, m, tap*Cin + ci) = src[b*a_batch_stride + (m*conv_stride + tap - pad)*lda + ci]

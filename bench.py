@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-chunks", type=int, default=4, help="chunks per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "none"], help="clock sampler during the timed region")
     return ap.parse_args()
 
 
@@ -109,45 +110,83 @@ def run_reference(args):
 # clocks sampler
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle-reason samples taken DURING the timed region, in-process through NVML
+    (nvidia_ml_py) from a background thread; `nvidia-smi -lms` in a subprocess is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index: int, mode: str = "nvml", period_s: float = 0.25):
+        self.idx, self.rows, self.proc, self.mode, self.period = gpu_index, [], None, mode, period_s
+        self.stop_flag = threading.Event()
+        self.thread = None
 
     def start(self):
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml as N
+
+                N.nvmlInit()
+                h = N.nvmlDeviceGetHandleByIndex(self.idx)
+                mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+                bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+                        "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                        "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+                        "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+
+                def loop():
+                    while not self.stop_flag.is_set():
+                        try:
+                            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                            pw = N.nvmlDeviceGetPowerUsage(h) / 1e3
+                            self.rows.append((float(sm), float(mx), pw, [k for k, b in bits.items() if r & b]))
+                        except Exception:
+                            pass
+                        self.stop_flag.wait(self.period)
+
+                self.thread = threading.Thread(target=loop, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(int(self.period * 1e3)), "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((float(r[1]), float(r[2]), float(r[3]),
+                                  [n for n, v in zip(names, r[5:9]) if v.lower().startswith("active")]))
+            except Exception:
+                pass
 
     def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        pw = [r[2] for r in self.rows]
+        reasons = sorted({x for r in self.rows for x in r[3]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "sm_mhz_min": min(sm) if sm else None,
+                "power_w_max": max(pw) if pw else None, "sampler": self.mode}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -226,18 +265,19 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         toks, lens = step()
     sync_all()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.sampler)
     sampler.start()
     launches0 = _lib.launch_count()
     phases = {"frontend_ms": 0.0, "encoder_ms": 0.0, "decode_ms": 0.0}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    step_ms = []
+    step_ms, step_decode_ms = [], []
     sync_all()
     e0.record()
     for _ in range(args.steps):
         toks, lens = step()
         tm = model.last_timing()
         step_ms.append(tm["total_ms"])
+        step_decode_ms.append(tm["decode_ms"])
         for k in phases:
             phases[k] += tm[k] / args.steps
     e1.record()
@@ -328,7 +368,7 @@ def run_b200(args):
                        "parallelism": f"chunks sharded x{world}, no data-path collective, final NCCL all_gather of ids",
                        "mean_tokens_per_chunk": mean_len},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "phases_ms_per_step": phases, "device_ms_each_step": step_ms,
+            "phases_ms_per_step": phases, "device_ms_each_step": step_ms, "decode_ms_each_step": step_decode_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

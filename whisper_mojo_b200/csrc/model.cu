@@ -229,12 +229,13 @@ int model_load(Model *m, const float *host, int64_t n_floats) {
 // ---------------------------------------------------------------------------------------------
 int model_logmel(Model *m, const float *pcm_dev, int n, float *mel_dev) {
     if (n <= 0) return WB_OK;
-    int *cmax = nullptr;
-    WB_CUDA(cudaMallocAsync((void **)&cmax, (size_t)n * sizeof(int), m->stream));
-    int rc = logmel_raw(m->stream, m->ft, pcm_dev, n, m->n_frames, mel_dev, cmax);
-    if (rc == WB_OK) rc = logmel_finalize(m->stream, mel_dev, cmax, n, m->NM, m->n_frames);
-    cudaFreeAsync(cmax, m->stream);
-    return rc;
+    if (n > m->cmax_cap) {  // per-chunk maxima (ordered-int encoding); grow-only, stays with the model
+        int *p = nullptr;
+        WB_CHECK(dalloc(m, &p, (size_t)n));
+        m->cmax = p, m->cmax_cap = n;
+    }
+    WB_CHECK(logmel_raw(m->stream, m->ft, pcm_dev, n, m->n_frames, mel_dev, m->cmax));
+    return logmel_finalize(m->stream, mel_dev, m->cmax, n, m->NM, m->n_frames);
 }
 
 // ---------------------------------------------------------------------------------------------

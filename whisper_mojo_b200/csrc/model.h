@@ -78,6 +78,8 @@ struct Model {
     struct Cache *tr_cache = nullptr;
     float *tr_mel = nullptr;
     size_t tr_mel_cap = 0;
+    int *cmax = nullptr;  // frontend: per-chunk log-mel maxima
+    int cmax_cap = 0;
     void *stage_in = nullptr, *stage_out = nullptr;  // host-API staging buffers (api.cu)
     size_t stage_in_cap = 0, stage_out_cap = 0;
 };

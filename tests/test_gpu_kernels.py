@@ -147,8 +147,10 @@ def test_cross_attention_absorbed_vs_fp64(B, S, D, H):
     assert np.abs(out - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max()), np.abs(out - ref).max()
 
 
-def test_logmel_frontend_matches_hf_golden_and_oracle():
+@pytest.mark.parametrize("impl", [1, 0], ids=["tf32x3_tensor_core", "fp32_fma"])
+def test_logmel_frontend_matches_hf_golden_and_oracle(impl):
     m = Whisper(WhisperConfig.tiny())
+    m.set_option("frontend_impl", impl)
     g = np.load(os.path.join(GOLDEN, "logmel_hf.npz"))
     a = synth.make_audio(int(g["n_chunks"]), seed=int(g["seed"]))
     mel = m.log_mel(a)
@@ -167,3 +169,22 @@ def test_logmel_frontend_matches_hf_golden_and_oracle():
     assert np.abs(me - re_).max() / max(re_.max() - re_.min(), 1.0) <= 1e-4
     assert np.all(me[0] == me[0, 0, 0]) and abs(me[0, 0, 0] - (-10 + 4) / 4) < 1e-6
     assert np.abs(me[2, :, :64] - g["short_first_frames"]).max() <= 1e-4
+
+
+def test_logmel_tensor_core_frontend_ragged_frames_and_loud_tone():
+    """Tensor-core frontend on a config whose 192 frames do not fill a 256-frame pair tile, and on a
+    full-scale tone over a 1e-4 noise floor (worst case for the split-precision DFT: weak bins next to a
+    dominant one, right at the -8 clamp)."""
+    cfg = WhisperConfig.micro()
+    m = Whisper(cfg)
+    a = np.random.default_rng(5).standard_normal((3, cfg.n_samples)).astype(np.float32) * 0.3
+    ref = LM.log_mel(a, n_samples=cfg.n_samples)
+    assert np.abs(m.log_mel(a) - ref).max() / (ref.max() - ref.min()) <= 1e-4
+    t = np.arange(480000) / 16000.0
+    tone = (0.9 * np.sin(2 * np.pi * 440.0 * t) + 1e-4 * np.random.default_rng(0).standard_normal(480000)).astype(np.float32)
+    mt = Whisper(WhisperConfig.tiny())
+    ref = LM.log_mel(tone[None])
+    got = mt.log_mel(tone[None])
+    assert np.abs(got - ref).max() / (ref.max() - ref.min()) <= 1e-4
+    mt.set_option("frontend_impl", 0)
+    assert np.abs(mt.log_mel(tone[None]) - got).max() <= 2e-4  # the two device frontends agree

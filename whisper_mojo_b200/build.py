@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libwhisper_b200.so")
-SOURCES = ["api.cu", "ops.cu", "gemm.cu", "kernels.cu", "frontend.cu", "model.cu", "attn_tc.cu", "cross_attn_tc.cu"]
+SOURCES = ["api.cu", "ops.cu", "gemm.cu", "kernels.cu", "frontend.cu", "frontend_tc.cu", "model.cu", "attn_tc.cu", "cross_attn_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
               "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -382,6 +382,7 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     WB_ARG(key, "null key");
     if (!strcmp(key, "gemm_impl")) m->gemm_impl = (int)value;
     else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
+    else if (!strcmp(key, "frontend_impl")) m->frontend_impl = (int)value;
     else if (!strcmp(key, "use_graph")) m->use_graph = (int)value;
     else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
     else if (!strcmp(key, "cross_impl")) {

@@ -208,6 +208,9 @@ static int upload(T **dst, const std::vector<T> &v) {
     return WB_OK;
 }
 
+int frontend_tc_tables_create(FrontendTables *t, const std::vector<std::vector<float>> &rows);  // frontend_tc.cu
+void frontend_tc_tables_destroy(FrontendTables *t);
+
 int frontend_tables_create(FrontendTables *t, int n_mels) {
     t->n_mels = n_mels;
     const double PI = 3.14159265358979323846;
@@ -227,6 +230,7 @@ int frontend_tables_create(FrontendTables *t, int n_mels) {
     for (int i = 0; i < n_mels + 2; i++) f_pts[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (n_mels + 1));
     std::vector<float> mw;
     std::vector<int> mstart(n_mels), mlen(n_mels), moff(n_mels);
+    std::vector<std::vector<float>> dense;
     for (int m = 0; m < n_mels; m++) {
         const double enorm = 2.0 / (f_pts[m + 2] - f_pts[m]);
         int first = -1, last = -1;
@@ -242,6 +246,7 @@ int frontend_tables_create(FrontendTables *t, int n_mels) {
                 last = k;
             }
         }
+        dense.push_back(row);
         if (first < 0) first = 0, last = -1;
         mstart[m] = first;
         mlen[m] = last - first + 1;
@@ -256,10 +261,11 @@ int frontend_tables_create(FrontendTables *t, int n_mels) {
     WB_CHECK(upload(&t->mel_start, mstart));
     WB_CHECK(upload(&t->mel_len, mlen));
     WB_CHECK(upload(&t->mel_off, moff));
-    return WB_OK;
+    return frontend_tc_tables_create(t, dense);
 }
 
 void frontend_tables_destroy(FrontendTables *t) {
+    frontend_tc_tables_destroy(t);
     cudaFree(t->tw_cos);
     cudaFree(t->tw_sin);
     cudaFree(t->window);
@@ -270,12 +276,13 @@ void frontend_tables_destroy(FrontendTables *t) {
     *t = FrontendTables();
 }
 
-int logmel_raw(cudaStream_t st, const FrontendTables &t, const float *pcm, int B, int n_frames, float *mel_raw,
-               int *chunk_max_enc) {
+int logmel_raw(cudaStream_t st, FrontendTables &t, const float *pcm, int B, int n_frames, float *mel_raw,
+               int *chunk_max_enc, int impl) {
     if (B <= 0) return WB_OK;
     WB_ARG(t.tw_cos && t.n_mels > 0, "frontend tables not initialised");
     logmel_init_max_kernel<<<cdiv(B, 256), 256, 0, st>>>(chunk_max_enc, B);
     WB_LAUNCHED();
+    if (impl == 1 && t.tc_ok) return logmel_raw_tc(st, t, pcm, B, n_frames, mel_raw, chunk_max_enc);
     const size_t smem = (size_t)(SEG + 2 * NFOLD * FR + FR) * sizeof(float);
     static bool opted = false;
     if (!opted) {

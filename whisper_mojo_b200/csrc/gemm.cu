@@ -614,6 +614,30 @@ int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
     return WB_OK;
 }
 
+// fp32 tensor map, 128-byte swizzle (box[0] = 32 elements); strides in bytes for dims 1..rank-1.
+int make_tmap_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                  const uint32_t *box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+        return WB_ERR_CUDA;
+    }
+    cuuint64_t d[3] = {1, 1, 1}, s[2] = {0, 0};
+    cuuint32_t b[3] = {1, 1, 1}, estr[3] = {1, 1, 1};
+    for (int i = 0; i < rank; i++) d[i] = dims[i], b[i] = box[i];
+    for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), d, s, b, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(f32) failed: %d (dims %llu,%llu,%llu strides %llu,%llu)", (int)r,
+                  (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)s[0],
+                  (unsigned long long)s[1]);
+        return WB_ERR_CUDA;
+    }
+    return WB_OK;
+}
+
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 template <int EPI>

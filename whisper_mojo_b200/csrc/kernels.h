@@ -77,12 +77,21 @@ struct FrontendTables {
     float *mel_w = nullptr;                      // sparse filterbank weights
     int *mel_start = nullptr, *mel_len = nullptr, *mel_off = nullptr;  // per mel bin
     int n_mels = 0;
+    // tensor-core frontend (frontend_tc.cu): TF32 hi / lo twiddles [416][416], per-DFT-bin filter view, workspace
+    bool tc_ok = false;
+    float *tc_b_hi = nullptr, *tc_b_lo = nullptr, *tc_bin_wa = nullptr, *tc_bin_wb = nullptr;
+    int *tc_bin_j = nullptr;
+    float *tc_ws = nullptr;  // reflect-padded hi / lo copies of the pcm, grow-only
+    size_t tc_ws_cap = 0;
 };
 int frontend_tables_create(FrontendTables *t, int n_mels);
 void frontend_tables_destroy(FrontendTables *t);
 // pcm f32 [B][n_frames*160] -> raw log10 mel f32 [B][n_mels][n_frames] and per-chunk max (ordered-int encoded).
-int logmel_raw(cudaStream_t st, const FrontendTables &t, const float *pcm, int B, int n_frames, float *mel_raw,
-               int *chunk_max_enc);
+// impl: 0 = fp32 FMA DFT (frontend.cu), 1 = TF32x3 tensor-core DFT (frontend_tc.cu) when the tables allow it.
+int logmel_raw(cudaStream_t st, FrontendTables &t, const float *pcm, int B, int n_frames, float *mel_raw,
+               int *chunk_max_enc, int impl = 1);
+int logmel_raw_tc(cudaStream_t st, FrontendTables &t, const float *pcm, int B, int n_frames, float *mel_raw,
+                  int *chunk_max_enc);
 // Finalise in place: v = (max(v, chunk_max - 8) + 4) / 4.
 int logmel_finalize(cudaStream_t st, float *mel, const int *chunk_max_enc, int B, int n_mels, int n_frames);
 // mel f32 [B][n_mels][n_frames] -> bf16 [B][n_frames][128] (channels >= n_mels zero) for the conv1 GEMM.

@@ -234,7 +234,7 @@ int model_logmel(Model *m, const float *pcm_dev, int n, float *mel_dev) {
         WB_CHECK(dalloc(m, &p, (size_t)n));
         m->cmax = p, m->cmax_cap = n;
     }
-    WB_CHECK(logmel_raw(m->stream, m->ft, pcm_dev, n, m->n_frames, mel_dev, m->cmax));
+    WB_CHECK(logmel_raw(m->stream, m->ft, pcm_dev, n, m->n_frames, mel_dev, m->cmax, m->frontend_impl));
     return logmel_finalize(m->stream, mel_dev, m->cmax, n, m->NM, m->n_frames);
 }
 

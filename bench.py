@@ -348,6 +348,41 @@ def run_b200(args):
     except Exception as ex:  # never lose the headline number to the profiling pass
         roofline = {"error": str(ex)}
 
+    # ---- phase rooflines: encoder on the tensor pipe, whole decode step and frontend on HBM ----
+    phase_roof = None
+    try:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        D, S, L, H, F, V = cfg.d_model, cfg.n_audio_ctx, cfg.n_layers, cfg.n_heads, 4 * cfg.d_model, cfg.vocab_size
+        enc_flop = (2 * cfg.n_frames * 3 * cfg.n_mels * D + 2 * S * 3 * D * D
+                    + L * (8 * S * D * D + 4 * S * S * D + 4 * S * D * F))  # 36.94 GFLOP for Tiny
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1340.0))
+        enc_tf = enc_flop * C / (phases["encoder_ms"] * 1e-3) / 1e12
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # decode: bytes one greedy step must move (bf16): weights touched once + per chunk the encoder output once
+        # per layer (absorbed cross-attention) + the self K/V rows written so far; averaged over the 196 forwards
+        n_fwd = 4 + cfg.max_iters
+        w_step = L * (4 * D * D + 2 * H * D * D + 2 * D * F) + V * D  # self qkv/o, folded cross q'/o', mlp, logits
+        t_avg = (n_fwd - 1) / 2.0
+        step_bytes = 2 * w_step + C * 2 * (L * S * D + 2 * L * t_avg * D)
+        dec_gbs = step_bytes * n_fwd / (phases["decode_ms"] * 1e-3) / 1e9
+        fe_bytes = C * (cfg.n_samples * 4 + cfg.n_mels * cfg.n_frames * 4)
+        phase_roof = {
+            "encoder": {"bound": "tensor", "achieved": enc_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": enc_tf / tf_peak,
+                        "flop_per_chunk": enc_flop, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "decode_step": {"bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": dec_gbs / hbm_peak, "bytes_per_step": step_bytes, "forwards": n_fwd},
+            "frontend": {"bound": "hbm", "achieved": fe_bytes / (phases["frontend_ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": fe_bytes / (phases["frontend_ms"] * 1e-3) / 1e9 / hbm_peak,
+                         "note": "pcm f32 in + log-mel f32 out; the TF32x3 DFT adds 2.9 GFLOP-equivalent per chunk",
+                         "dft_tflops_tf32": 3 * 2 * cfg.n_frames * 416 * 416 * C / (phases["frontend_ms"] * 1e-3) / 1e12},
+        }
+    except Exception as ex:
+        phase_roof = {"error": str(ex)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, dt, cores, _ = cpu_transcribe_rate(args.cpu_chunks)
@@ -364,10 +399,11 @@ def run_b200(args):
                                    f"{C} synthetic 30 s chunks per GPU per step, pcm -> log-mel -> encoder -> "
                                    "196 decoder forwards (EOT never fires with random weights)",
                        "chunks_per_gpu": C, "global_chunks": n_total, "weights": "random-init whisper-tiny shapes, seed 0",
-                       "l2": "inputs (pcm %.1f GB per GPU) larger than L2; no explicit flush" % (pcm.numel() * 4 / 1e9),
+                       "l2": "inputs (pcm %.1f GB per GPU) larger than the 126 MB L2; no explicit flush" % (pcm.numel() * 4 / 1e9),
                        "parallelism": f"chunks sharded x{world}, no data-path collective, final NCCL all_gather of ids",
                        "mean_tokens_per_chunk": mean_len},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "phase_rooflines": phase_roof,
+            "cpu_baseline": cpu,
             "phases_ms_per_step": phases, "device_ms_each_step": step_ms, "decode_ms_each_step": step_decode_ms,
         }
         print(json.dumps(line), flush=True)

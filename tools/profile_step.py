@@ -19,12 +19,15 @@ ap.add_argument("--iters", type=int, default=8)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--graph", type=int, default=0)
 ap.add_argument("--lanes", type=int, default=2)
+ap.add_argument("--enc-batch", type=int, default=0)
 a = ap.parse_args()
 base = WhisperConfig.tiny()
 cfg = WhisperConfig(**{**base.__dict__, "max_iters": a.iters})
 m = Whisper(cfg, stream=torch.cuda.current_stream().cuda_stream)
 m.set_option("use_graph", a.graph)
 m.set_option("decode_lanes", a.lanes)
+if a.enc_batch:
+    m.set_option("enc_batch", a.enc_batch)
 m.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
 pcm = synth_pcm_gpu(a.chunks, cfg.n_samples, torch.device("cuda"), 1234)
 for r in range(a.reps):

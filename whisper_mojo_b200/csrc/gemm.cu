@@ -14,6 +14,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -423,28 +424,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 //   * each CTA's eight epilogue warps drain their own TMEM (128 lanes x BN2 columns) and arrive on the
 //     leader's "accumulator empty" barrier (remote arrive for the peer).
 // ---------------------------------------------------------------------------------------------
-static constexpr int PAIR_STAGES = 6, PAIR_STAGE_BYTES = 32768;  // A 16 KB + B up to 16 KB per CTA
-static constexpr int PAIR_SMEM_BYTES = 1024 + PAIR_STAGES * PAIR_STAGE_BYTES + 256 + 8 * 128 * 4;
+static constexpr int PAIR_STAGE_BYTES = 32768;  // A 16 KB + B up to 16 KB per CTA
+// 6 ring stages; the TMA-output variant trades two of them for the epilogue staging tiles (8 warps x 2 x 4 KB)
+static constexpr int pair_stages(bool tma_out) { return tma_out ? 4 : 6; }
+static constexpr int pair_smem_bytes(bool tma_out) {
+    return 1024 + pair_stages(tma_out) * PAIR_STAGE_BYTES + 256 + 8 * 128 * 4 + (tma_out ? 8 * 2 * 4096 : 0);
+}
 
 struct GemmPairParams {
     CUtensorMap a_map[3];
     CUtensorMap b_map;  // box {64, BN2/2}
     GemmDev d;
     int pair_tiles_m_per_batch, pair_tiles_n;
+    CUtensorMap out_map;  // TMA_OUT: fp32 output as {N, rows_per_batch, batches}, box {32, 32, 1}, 128B swizzle
 };
 
-template <int EPI, int BN2>
+// TMA_OUT (EPI_RESID_F32 with a plain [rows][N] output): the residual add is done by the L2 -- each epilogue
+// warp stages its 32 x 32 fp32 tile (acc + bias) in swizzled shared memory and issues one
+// cp.reduce.async.bulk.tensor (.add.f32) per tile; the SM never reads the old values, so no HBM latency sits
+// in the epilogue and the stores are full 128-byte rows.  One add per element: bit-identical to x + (acc + bias).
+template <int EPI, int BN2, bool TMA_OUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_pair_kernel(const __grid_constant__ GemmPairParams P) {
+    constexpr int PAIR_STAGES = pair_stages(TMA_OUT);
     extern __shared__ uint8_t smem_raw[];
     const GemmDev &p = P.d;
     constexpr int B_ROWS = BN2 / 2, B_BYTES = B_ROWS * BK * 2;
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + PAIR_STAGES * PAIR_STAGE_BYTES);
+    // [ring][TMA_OUT: 8 warps x 2 staging tiles of 4 KB, 1024-byte aligned as the 128B swizzle requires][barriers][bias]
+    constexpr int RING_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + (TMA_OUT ? 8 * 2 * 4096 : 0);
+    uint8_t *stage_out = tiles + PAIR_STAGES * PAIR_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + RING_BYTES);
     uint64_t *full_bar = bars, *empty_bar = bars + PAIR_STAGES;
     uint64_t *tmem_full = bars + 2 * PAIR_STAGES, *tmem_empty = bars + 2 * PAIR_STAGES + 2;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * PAIR_STAGES + 4);
-    float *bias_smem = reinterpret_cast<float *>(tiles + PAIR_STAGES * PAIR_STAGE_BYTES + 256);  // [8][128]
+    float *bias_smem = reinterpret_cast<float *>(tiles + RING_BYTES + 256);  // [8][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -454,6 +468,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (warp == 0 && lane == 0) {
         for (int t = 0; t < p.taps; t++) ptx::prefetch_tmap(&P.a_map[t]);
         ptx::prefetch_tmap(&P.b_map);
+        if (TMA_OUT) ptx::prefetch_tmap(&P.out_map);
         for (int s = 0; s < PAIR_STAGES; s++) {
             ptx::mbar_init(&full_bar[s], 1);   // used on the leader only
             ptx::mbar_init(&empty_bar[s], 1);  // one multicast commit per use
@@ -529,6 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         constexpr int CH = BN2 / 64;  // 32-column chunks per half
         float *sbias = bias_smem + (warp - 2) * 128;
         int it = 0;
+        uint32_t out_ctr = 0;  // staging-buffer parity (TMA_OUT)
         for (int tile = pair_id; tile < total_tiles; tile += n_pairs, it++) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -546,24 +562,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             EpiChunk<EPI> e[2];
             uint32_t v[2][32];
             ptx::tmem_ld_32x32b_x32(taddr, v[0]);
-            epi_prefetch<EPI>(p, b, m, n_first, e[0]);
+            if (!TMA_OUT) epi_prefetch<EPI>(p, b, m, n_first, e[0]);
             stage_bias(p, n_first, BN2 / 2, sbias, lane);
 #pragma unroll
             for (int c = 0; c < CH; c++) {
                 ptx::tmem_ld_wait();  // chunk c is in v[c & 1]
                 if (c + 1 < CH) {
                     ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-                    epi_prefetch<EPI>(p, b, m, n_first + (c + 1) * 32, e[(c + 1) & 1]);
+                    if (!TMA_OUT) epi_prefetch<EPI>(p, b, m, n_first + (c + 1) * 32, e[(c + 1) & 1]);
                 } else {
                     // the whole accumulator slice has left TMEM: hand the buffer back before the last stores
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster_relaxed(ptx::mapa_u32(&tmem_empty[acc], 0));
                 }
-                epi_finish<EPI>(p, b, m, n_first + c * 32, v[c & 1], e[c & 1], sbias + c * 32, best, best_idx);
+                if (TMA_OUT) {
+                    // 32 rows x 32 fp32 -> this warp's staging tile (rows of 128 B, 16-byte chunks XOR-swizzled by
+                    // row & 7 exactly as the tensor map's 128B swizzle expects), then one bulk reduce-add
+                    uint8_t *buf = stage_out + ((warp - 2) * 2 + (out_ctr & 1)) * 4096;
+                    if (lane == 0) ptx::bulk_wait_group_read<1>();  // the store that last used this buffer has read it
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(sbias + c * 32 + 4 * j);
+                        float4 o;
+                        o.x = __uint_as_float(v[c & 1][4 * j]) + bv.x, o.y = __uint_as_float(v[c & 1][4 * j + 1]) + bv.y;
+                        o.z = __uint_as_float(v[c & 1][4 * j + 2]) + bv.z, o.w = __uint_as_float(v[c & 1][4 * j + 3]) + bv.w;
+                        *reinterpret_cast<float4 *>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int m_w = (mt % P.pair_tiles_m_per_batch) * 256 + (int)rank * BM + q * 32;
+                        ptx::tma_reduce_add_3d(&P.out_map, buf, n_first + c * 32, m_w, b);
+                        ptx::bulk_commit_group();
+                    }
+                    out_ctr++;
+                } else {
+                    epi_finish<EPI>(p, b, m, n_first + c * 32, v[c & 1], e[c & 1], sbias + c * 32, best, best_idx);
+                }
             }
         }
     }
+    if (TMA_OUT && warp >= 2 && lane == 0) ptx::bulk_wait_group<0>();  // staged tiles fully written before exit
     ptx::tc_fence_before();
     ptx::cluster_sync();  // the peer may still signal this CTA's barriers / read its shared memory
     if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 512);
@@ -652,26 +693,28 @@ static int launch_tc(cudaStream_t st, const GemmTcParams &P, int grid) {
     return WB_OK;
 }
 
-template <int EPI, int BN2>
+template <int EPI, int BN2, bool TMA_OUT>
 static int launch_pair(cudaStream_t st, const GemmPairParams &P, int grid) {
     static bool attr_set = false;
+    constexpr int smem = pair_smem_bytes(TMA_OUT);
     if (!attr_set) {
-        WB_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     PAIR_SMEM_BYTES));
+        WB_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BN2, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    gemm_pair_kernel<EPI, BN2><<<grid, TC_THREADS, PAIR_SMEM_BYTES, st>>>(P);
+    gemm_pair_kernel<EPI, BN2, TMA_OUT><<<grid, TC_THREADS, smem, st>>>(P);
     WB_LAUNCHED();
     return WB_OK;
 }
-template <int EPI>
+template <int EPI, bool TMA_OUT = false>
 static int launch_pair_bn(cudaStream_t st, const GemmPairParams &P, int grid, int bn2) {
     switch (bn2) {
-        case 256: return launch_pair<EPI, 256>(st, P, grid);
-        case 192: return launch_pair<EPI, 192>(st, P, grid);
-        default: return launch_pair<EPI, 128>(st, P, grid);
+        case 256: return launch_pair<EPI, 256, TMA_OUT>(st, P, grid);
+        case 192: return launch_pair<EPI, 192, TMA_OUT>(st, P, grid);
+        default: return launch_pair<EPI, 128, TMA_OUT>(st, P, grid);
     }
 }
+
+bool g_resid_tma = true;  // A/B switch (WB_RESID_TMA=0 in the environment restores the load-add-store epilogue)
 
 // Pair-tile width: the widest of 256 / 192 / 128 that wastes the fewest padded columns.
 static int pick_pair_bn(int N) {
@@ -750,6 +793,12 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
+    static const bool env_once = [] {
+        const char *e = getenv("WB_RESID_TMA");
+        if (e && e[0] == '0') g_resid_tma = false;
+        return true;
+    }();
+    (void)env_once;
     // CTA-pair kernel for the large GEMMs (encoder, cross-K/V): at least one full wave of 256-row pair tiles.
     const int pair_tiles_m = cdiv(d.rows_per_batch, 256);
     const bool pair_ok = d.epi != EPI_ARGMAX;
@@ -768,7 +817,17 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
         switch (d.epi) {
             case EPI_STORE_BF16: return launch_pair_bn<EPI_STORE_BF16>(st, Q, grid, bn2);
             case EPI_GELU_BF16: return launch_pair_bn<EPI_GELU_BF16>(st, Q, grid, bn2);
-            case EPI_RESID_F32: return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
+            case EPI_RESID_F32: {
+                // plain [rows][N] fp32 output -> residual add by TMA reduce (no read of the old values in the SM)
+                const bool plain = d.n_seg_ptrs == 1 && !d.dyn_off && p.seg_cols == d.N && (d.out_ld[0] % 4) == 0 &&
+                                   (reinterpret_cast<uintptr_t>(d.out[0]) & 15) == 0 && g_resid_tma;
+                if (!plain) return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
+                const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.rows_per_batch, (uint64_t)d.batches};
+                const uint64_t str[2] = {(uint64_t)d.out_ld[0] * 4, (uint64_t)d.rows_per_batch * d.out_ld[0] * 4};
+                const uint32_t box[3] = {32, 32, 1};
+                WB_CHECK(make_tmap_f32(&Q.out_map, d.out[0], 3, dims, str, box));
+                return launch_pair_bn<EPI_RESID_F32, true>(st, Q, grid, bn2);
+            }
             case EPI_STORE_F32: return launch_pair_bn<EPI_STORE_F32>(st, Q, grid, bn2);
             case EPI_GELU_POS_F32: return launch_pair_bn<EPI_GELU_POS_F32>(st, Q, grid, bn2);
         }

@@ -87,6 +87,25 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
         : "memory");
 }
 
+// Bulk tensor reduction shared -> global: global[tile] += smem tile (element type and swizzle from the tensor
+// map); completion is tracked per thread through bulk async-groups.
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+            reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {  // at most N groups still reading their shared-memory source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- tcgen05 / TMEM --------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_holder, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),

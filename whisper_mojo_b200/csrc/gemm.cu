@@ -439,10 +439,11 @@ struct GemmPairParams {
     CUtensorMap out_map;  // TMA_OUT: fp32 output as {N, rows_per_batch, batches}, box {32, 32, 1}, 128B swizzle
 };
 
-// TMA_OUT (EPI_RESID_F32 with a plain [rows][N] output): the residual add is done by the L2 -- each epilogue
-// warp stages its 32 x 32 fp32 tile (acc + bias) in swizzled shared memory and issues one
-// cp.reduce.async.bulk.tensor (.add.f32) per tile; the SM never reads the old values, so no HBM latency sits
-// in the epilogue and the stores are full 128-byte rows.  One add per element: bit-identical to x + (acc + bias).
+// TMA_OUT (plain [rows][N] outputs): each epilogue warp stages its 32 x 32 tile in swizzled shared memory and
+// issues one bulk tensor store per tile -- full-row writes instead of 32 scattered 16-byte stores per
+// instruction.  For EPI_RESID_F32 the store is a cp.reduce.async.bulk.tensor (.add.f32): the residual add is
+// done by the L2, the SM never reads the old values, so no HBM latency sits in the epilogue.  One add per
+// element: bit-identical to x + (acc + bias).
 template <int EPI, int BN2, bool TMA_OUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_pair_kernel(const __grid_constant__ GemmPairParams P) {
@@ -577,24 +578,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                     if (lane == 0) ptx::mbar_arrive_cluster_relaxed(ptx::mapa_u32(&tmem_empty[acc], 0));
                 }
                 if (TMA_OUT) {
-                    // 32 rows x 32 fp32 -> this warp's staging tile (rows of 128 B, 16-byte chunks XOR-swizzled by
-                    // row & 7 exactly as the tensor map's 128B swizzle expects), then one bulk reduce-add
+                    // 32 rows x 32 values -> this warp's staging tile, 16-byte chunks XOR-swizzled exactly as the
+                    // output tensor map expects (fp32: 128 B rows / 128B swizzle, bf16: 64 B rows / 64B swizzle),
+                    // then one bulk tensor store (bf16) or reduce-add (fp32 residual) per tile
                     uint8_t *buf = stage_out + ((warp - 2) * 2 + (out_ctr & 1)) * 4096;
                     if (lane == 0) ptx::bulk_wait_group_read<1>();  // the store that last used this buffer has read it
                     __syncwarp();
+                    float o[32];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const float4 bv = *reinterpret_cast<const float4 *>(sbias + c * 32 + 4 * j);
-                        float4 o;
-                        o.x = __uint_as_float(v[c & 1][4 * j]) + bv.x, o.y = __uint_as_float(v[c & 1][4 * j + 1]) + bv.y;
-                        o.z = __uint_as_float(v[c & 1][4 * j + 2]) + bv.z, o.w = __uint_as_float(v[c & 1][4 * j + 3]) + bv.w;
-                        *reinterpret_cast<float4 *>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                        o[4 * j] = __uint_as_float(v[c & 1][4 * j]) + bv.x, o[4 * j + 1] = __uint_as_float(v[c & 1][4 * j + 1]) + bv.y;
+                        o[4 * j + 2] = __uint_as_float(v[c & 1][4 * j + 2]) + bv.z, o[4 * j + 3] = __uint_as_float(v[c & 1][4 * j + 3]) + bv.w;
+                    }
+                    if (EPI == EPI_RESID_F32) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            *reinterpret_cast<float4 *>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    } else {
+                        if (EPI == EPI_GELU_BF16) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) o[j] = gelu_fast(o[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            *reinterpret_cast<uint4 *>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
+                                           pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
                     }
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         const int m_w = (mt % P.pair_tiles_m_per_batch) * 256 + (int)rank * BM + q * 32;
-                        ptx::tma_reduce_add_3d(&P.out_map, buf, n_first + c * 32, m_w, b);
+                        if (EPI == EPI_RESID_F32) ptx::tma_reduce_add_3d(&P.out_map, buf, n_first + c * 32, m_w, b);
+                        else ptx::tma_store_3d(&P.out_map, buf, n_first + c * 32, m_w, b);
                         ptx::bulk_commit_group();
                     }
                     out_ctr++;
@@ -655,9 +673,9 @@ int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
     return WB_OK;
 }
 
-// fp32 tensor map, 128-byte swizzle (box[0] = 32 elements); strides in bytes for dims 1..rank-1.
-int make_tmap_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                  const uint32_t *box) {
+// Generic tiled tensor map; strides in bytes for dims 1..rank-1.  swizzle_bytes in {0, 32, 64, 128}.
+static int make_tmap_any(CUtensorMap *map, CUtensorMapDataType dtype, int swizzle_bytes, const void *base, int rank,
+                         const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -667,16 +685,24 @@ int make_tmap_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *
     cuuint32_t b[3] = {1, 1, 1}, estr[3] = {1, 1, 1};
     for (int i = 0; i < rank; i++) d[i] = dims[i], b[i] = box[i];
     for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), d, s, b, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(map, dtype, (cuuint32_t)rank, const_cast<void *>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled(f32) failed: %d (dims %llu,%llu,%llu strides %llu,%llu)", (int)r,
+        set_error("cuTensorMapEncodeTiled failed: %d (dims %llu,%llu,%llu strides %llu,%llu)", (int)r,
                   (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)s[0],
                   (unsigned long long)s[1]);
         return WB_ERR_CUDA;
     }
     return WB_OK;
+}
+// fp32 tensor map, 128-byte swizzle (box[0] = 32 elements).
+int make_tmap_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                  const uint32_t *box) {
+    return make_tmap_any(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 128, base, rank, dims, strides_bytes, box);
 }
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -714,7 +740,7 @@ static int launch_pair_bn(cudaStream_t st, const GemmPairParams &P, int grid, in
     }
 }
 
-bool g_resid_tma = true;  // A/B switch (WB_RESID_TMA=0 in the environment restores the load-add-store epilogue)
+bool g_tma_out = true;  // A/B switch (WB_TMA_OUT=0 in the environment restores the per-thread store epilogues)
 
 // Pair-tile width: the widest of 256 / 192 / 128 that wastes the fewest padded columns.
 static int pick_pair_bn(int N) {
@@ -794,8 +820,8 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
     static const bool env_once = [] {
-        const char *e = getenv("WB_RESID_TMA");
-        if (e && e[0] == '0') g_resid_tma = false;
+        const char *e = getenv("WB_TMA_OUT");
+        if (e && e[0] == '0') g_tma_out = false;
         return true;
     }();
     (void)env_once;
@@ -815,18 +841,27 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
         const int total = d.batches * pair_tiles_m * Q.pair_tiles_n;
         const int grid = 2 * std::min(total, sms / 2);
         switch (d.epi) {
-            case EPI_STORE_BF16: return launch_pair_bn<EPI_STORE_BF16>(st, Q, grid, bn2);
-            case EPI_GELU_BF16: return launch_pair_bn<EPI_GELU_BF16>(st, Q, grid, bn2);
+            case EPI_STORE_BF16:
+            case EPI_GELU_BF16:
             case EPI_RESID_F32: {
-                // plain [rows][N] fp32 output -> residual add by TMA reduce (no read of the old values in the SM)
-                const bool plain = d.n_seg_ptrs == 1 && !d.dyn_off && p.seg_cols == d.N && (d.out_ld[0] % 4) == 0 &&
-                                   (reinterpret_cast<uintptr_t>(d.out[0]) & 15) == 0 && g_resid_tma;
-                if (!plain) return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
-                const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.rows_per_batch, (uint64_t)d.batches};
-                const uint64_t str[2] = {(uint64_t)d.out_ld[0] * 4, (uint64_t)d.rows_per_batch * d.out_ld[0] * 4};
-                const uint32_t box[3] = {32, 32, 1};
-                WB_CHECK(make_tmap_f32(&Q.out_map, d.out[0], 3, dims, str, box));
-                return launch_pair_bn<EPI_RESID_F32, true>(st, Q, grid, bn2);
+                // plain [rows][N] output -> coalesced TMA stores (bf16) / residual add by TMA reduce (fp32: the SM
+                // never reads the old values)
+                const int esz = d.epi == EPI_RESID_F32 ? 4 : 2;
+                const bool plain = d.n_seg_ptrs == 1 && !d.dyn_off && p.seg_cols == d.N && (d.out_ld[0] * esz) % 16 == 0 &&
+                                   (reinterpret_cast<uintptr_t>(d.out[0]) & 15) == 0 && g_tma_out;
+                if (plain) {
+                    const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.rows_per_batch, (uint64_t)d.batches};
+                    const uint64_t str[2] = {(uint64_t)d.out_ld[0] * esz, (uint64_t)d.rows_per_batch * d.out_ld[0] * esz};
+                    const uint32_t box[3] = {32, 32, 1};
+                    WB_CHECK(make_tmap_any(&Q.out_map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                           esz == 4 ? 128 : 64, d.out[0], 3, dims, str, box));
+                    if (d.epi == EPI_STORE_BF16) return launch_pair_bn<EPI_STORE_BF16, true>(st, Q, grid, bn2);
+                    if (d.epi == EPI_GELU_BF16) return launch_pair_bn<EPI_GELU_BF16, true>(st, Q, grid, bn2);
+                    return launch_pair_bn<EPI_RESID_F32, true>(st, Q, grid, bn2);
+                }
+                if (d.epi == EPI_STORE_BF16) return launch_pair_bn<EPI_STORE_BF16>(st, Q, grid, bn2);
+                if (d.epi == EPI_GELU_BF16) return launch_pair_bn<EPI_GELU_BF16>(st, Q, grid, bn2);
+                return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
             }
             case EPI_STORE_F32: return launch_pair_bn<EPI_STORE_F32>(st, Q, grid, bn2);
             case EPI_GELU_POS_F32: return launch_pair_bn<EPI_GELU_POS_F32>(st, Q, grid, bn2);

@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-chunks", type=int, default=4, help="chunks per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=1, help="decode lanes (2 = two half-batches on two streams)")
     ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "none"], help="clock sampler during the timed region")
     return ap.parse_args()
 
@@ -215,11 +216,11 @@ def synth_pcm_gpu(n, n_samples, device, seed):
 
 def ncu_traffic(chunks):
     """dram__bytes_read.sum + dram__bytes_write.sum per cross-attention launch from the committed
-    `ncu --set full` capture (profiles/), valid for the chunk count it was captured at; else None."""
+    `ncu --set full` capture (profiles/), valid for the chunk count it was captured at (2048); else None."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_cross_attn_absorbed_ncu_full.json")))
-        if d["algorithmic_bytes_per_launch"] == chunks * (1500 * 384 + 2 * 6 * 384) * 2:
-            return d["cross_attention_traffic_bytes_per_launch"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_cross_attn_absorbed_ncu_full_v2.json")))
+        if chunks == 2048 and "2048" in d["command"]:
+            return d["dram_traffic_bytes_per_launch_mean"]
     except Exception:
         pass
     return None
@@ -248,6 +249,8 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
     model = Whisper(cfg, stream=stream.cuda_stream)
     model.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
+    if args.lanes != 1:
+        model.set_option("decode_lanes", args.lanes)
     pcm = synth_pcm_gpu(C, cfg.n_samples, dev, seed=1234 + rank)  # 3.9 GB at C=2048: larger than the 126 MB L2
     n_total = C * world
 
@@ -325,7 +328,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         tot_ms, n_launch = model.last_cross_attention_timing()
         model.set_option("profile_attn", 0)
-        model.set_option("decode_lanes", 1)
+        model.set_option("decode_lanes", args.lanes)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

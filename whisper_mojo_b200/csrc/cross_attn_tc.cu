@@ -78,10 +78,16 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
     uint8_t *sQ = base + 2 * stage_bytes;                  // [atoms][16 x 64]
     uint8_t *sP = sQ + XA_MAX_ATOMS * QATOM_BYTES;         // [2][16 x 64]   P^T, keys 0-63 | 64-127
     uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * QATOM_BYTES);
-    uint64_t *enc_full = bars, *enc_empty = bars + 2, *q_full = bars + 4, *q_empty = bars + 5, *s_full = bars + 6,
-             *s_empty = bars + 8, *p_full = bars + 10, *c_done = bars + 11, *c_empty = bars + 12;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 13);
-    float *s_red = reinterpret_cast<float *>(bars + 14);  // [4 warps][16] cross-warp reduction scratch
+    // enc_full[stage][atom]: one barrier per 64-channel atom, so the score MMAs of an atom issue as soon as it has
+    // landed instead of after the whole 96 KB stage (the S MMAs are issue bound: ~1 us per block otherwise sits
+    // between "stage arrived" and "scores ready", and with only two stages that latency caps the HBM stream)
+    // enc_empty[stage][atom pair]: the context MMAs walk the atom pairs in order and release each pair as soon as
+    // its 8 MMAs are done, so the refill of the stage starts ~0.7 us before the block's last MMA retires
+    uint64_t *enc_full = bars, *enc_empty = bars + 2 * XA_MAX_ATOMS, *q_full = enc_empty + XA_MAX_ATOMS, *q_empty = q_full + 1,
+             *s_full = q_empty + 1, *s_empty = s_full + 2, *p_full = s_empty + 2, *c_done = p_full + 1,
+             *c_empty = c_done + 1;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(c_empty + 1);
+    float *s_red = reinterpret_cast<float *>(c_empty + 2);  // [4 warps][16] cross-warp reduction scratch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = P.n_blocks, D = P.D;
@@ -91,9 +97,9 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&P.enc_map);
         ptx::prefetch_tmap(&P.q_map);
+        for (int i = 0; i < 2 * XA_MAX_ATOMS; i++) ptx::mbar_init(&enc_full[i], 1);
+        for (int i = 0; i < XA_MAX_ATOMS; i++) ptx::mbar_init(&enc_empty[i], 1);
         for (int i = 0; i < 2; i++) {
-            ptx::mbar_init(&enc_full[i], 1);
-            ptx::mbar_init(&enc_empty[i], 1);
             ptx::mbar_init(&s_full[i], 1);
             ptx::mbar_init(&s_empty[i], 4);
         }
@@ -127,12 +133,13 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 for (int a = 0; a < atoms; a++) ptx::tma_load_3d(sQ + a * QATOM_BYTES, &P.q_map, q_full, a * 64, 0, b);
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
-                    ptx::mbar_wait(&enc_empty[s], ((g >> 1) & 1) ^ 1);
-                    XA_STAMP(0, g, 0);
-                    ptx::mbar_expect_tx(&enc_full[s], stage_bytes);
-                    for (int a = 0; a < atoms; a++)
-                        ptx::tma_load_3d(sEnc + s * stage_bytes + a * ATOM_BYTES, &P.enc_map, &enc_full[s], a * 64,
-                                         j * 128, b);
+                    for (int a = 0; a < atoms; a++) {
+                        if ((a & 1) == 0) ptx::mbar_wait(&enc_empty[s * (XA_MAX_ATOMS / 2) + (a >> 1)], ((g >> 1) & 1) ^ 1);
+                        if (a == 0) XA_STAMP(0, g, 0);
+                        uint64_t *bar = &enc_full[s * XA_MAX_ATOMS + a];
+                        ptx::mbar_expect_tx(bar, ATOM_BYTES);
+                        ptx::tma_load_3d(sEnc + s * stage_bytes + a * ATOM_BYTES, &P.enc_map, bar, a * 64, j * 128, b);
+                    }
                 }
             }
         }
@@ -147,19 +154,18 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 ptx::mbar_wait(q_full, ci & 1);
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
-                    ptx::mbar_wait(&enc_full[s], (g >> 1) & 1);
-                    XA_STAMP(1, g, 0);
                     ptx::mbar_wait(&s_empty[s], ((g >> 1) & 1) ^ 1);
                     XA_STAMP(1, g, 1);
-                    ptx::tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 8; kk++) {  // 8 K-steps of 16 channels inside an atom pair
+                    for (int a = 0; a < atoms; a++) {  // atoms in arrival order; atom pair `part` shares an accumulator
+                        ptx::mbar_wait(&enc_full[s * XA_MAX_ATOMS + a], (g >> 1) & 1);
+                        if (a == 0) XA_STAMP(1, g, 0);
+                        ptx::tc_fence_after();
+                        const int part = a >> 1;
 #pragma unroll
-                        for (int part = 0; part < n_acc; part++) {
-                            const int a = 2 * part + (kk >> 2), k = kk & 3;  // descriptors advance in 16-byte units
+                        for (int k = 0; k < 4; k++)  // 4 K-steps of 16 channels; descriptors advance in 16-byte units
                             ptx::mma_bf16_ss(tS0 + 16 * (s * n_acc + part), a_desc0[s] + a * (ATOM_BYTES >> 4) + 2 * k,
-                                             b_desc0 + a * (QATOM_BYTES >> 4) + 2 * k, idesc_s, kk != 0);
-                        }
+                                             b_desc0 + a * (QATOM_BYTES >> 4) + 2 * k, idesc_s, ((a & 1) | k) != 0);
                     }
                     ptx::mma_commit(&s_full[s]);
                     if (j + 1 == nblk) ptx::mma_commit(q_empty);
@@ -185,13 +191,13 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                     XA_STAMP(1, g, 2);
                     ptx::tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
+                    for (int m = 0; m < n_acc; m++) {  // atom pair m = channels [128 m, 128 m + 128)
 #pragma unroll
-                        for (int m = 0; m < n_acc; m++)  // consecutive MMAs hit different accumulators
+                        for (int k = 0; k < 8; k++)
                             ptx::mma_bf16_ss(tC0 + 32 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
                                              p_desc0 + (k >> 2) * (QATOM_BYTES >> 4) + 2 * (k & 3), idesc_c, (j | k) != 0);
+                        ptx::mma_commit(&enc_empty[s * (XA_MAX_ATOMS / 2) + m]);
                     }
-                    ptx::mma_commit(&enc_empty[s]);
                     ptx::mma_commit(c_done);
                     XA_STAMP(1, g, 3);
                 }
@@ -335,7 +341,8 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
 
 size_t cross_attn_absorbed_smem(int D) {
     const int atoms = D / 64;
-    return 1024 + (size_t)2 * atoms * ATOM_BYTES + XA_MAX_ATOMS * QATOM_BYTES + 2 * QATOM_BYTES + 14 * 8 + 64 * 4 + 64;
+    return 1024 + (size_t)2 * atoms * ATOM_BYTES + XA_MAX_ATOMS * QATOM_BYTES + 2 * QATOM_BYTES +
+           (3 * XA_MAX_ATOMS + 12) * 8 + 64 * 4 + 64;
 }
 
 bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 384 && H <= 16; }

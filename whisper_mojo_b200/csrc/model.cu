@@ -396,8 +396,10 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
         ln.g.scalars = c->scalars + 4 * i;
         ln.g.T_out = T_out, ln.g.eot = m->cfg.eot, ln.g.pos_quirk = m->cfg.pos_quirk;
     }
-    if (ok && cudaMallocHost((void **)&c->pinned_scalars, 8 * sizeof(int)) != cudaSuccess) {
-        set_error("kvcache: pinned allocation failed");
+    if (ok && (cudaMallocHost((void **)&c->pinned_scalars, 16 * sizeof(int)) != cudaSuccess ||
+               cudaEventCreateWithFlags(&c->poll_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+               cudaEventCreateWithFlags(&c->poll_ev[1], cudaEventDisableTiming) != cudaSuccess)) {
+        set_error("kvcache: pinned allocation / event creation failed");
         ok = false;
     }
     if (!ok) {
@@ -417,6 +419,8 @@ void cache_destroy(Cache *c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (void *p : c->owned) cudaFree(p);
     if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
+    for (cudaEvent_t e : c->poll_ev)
+        if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -596,13 +600,23 @@ static int greedy_loop(Cache *c) {
         WB_CUDA(cudaGraphInstantiate(&c->graph_exec, gr, 0));
         cudaGraphDestroy(gr);
     }
+    // `if next_token == 50257: break` (whisper.mojo:207), batched: stop once every chunk has produced EOT.  The
+    // done counters are snapshotted every 16 steps and the host looks at the PREVIOUS snapshot, so a block of
+    // steps is always queued behind the one being checked and host jitter never idles the GPU (finished
+    // chunks ignore the extra steps: greedy_advance is a no-op for them).
+    int blk = 0;
     for (int it = 0; it < m->cfg.max_iters; it++) {  // whisper.mojo:205
-        if ((it & 15) == 0) {                         // `if next_token == 50257: break`, polled every 16 steps
-            WB_CUDA(cudaMemcpyAsync(c->pinned_scalars, c->scalars, 4 * n_lanes * sizeof(int), cudaMemcpyDeviceToHost, st));
-            WB_CUDA(cudaStreamSynchronize(st));
-            int n_done = 0;
-            for (int i = 0; i < n_lanes; i++) n_done += c->pinned_scalars[4 * i + 2];
-            if (n_done >= c->B) break;
+        if ((it & 15) == 0) {
+            WB_CUDA(cudaMemcpyAsync(c->pinned_scalars + 8 * (blk & 1), c->scalars, 4 * n_lanes * sizeof(int),
+                                    cudaMemcpyDeviceToHost, st));
+            WB_CUDA(cudaEventRecord(c->poll_ev[blk & 1], st));
+            if (blk >= 1) {
+                WB_CUDA(cudaEventSynchronize(c->poll_ev[(blk - 1) & 1]));
+                int n_done = 0;
+                for (int i = 0; i < n_lanes; i++) n_done += c->pinned_scalars[8 * ((blk - 1) & 1) + 4 * i + 2];
+                if (n_done >= c->B) break;
+            }
+            blk++;
         }
         if (graph) {
             WB_CUDA(cudaGraphLaunch(c->graph_exec, st));
@@ -645,7 +659,9 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
     const size_t in_per = mel_dev ? mel_per : (size_t)m->n_samples;
     float *in_dev = const_cast<float *>(mel_dev ? mel_dev : pcm_dev);
     int wave = std::min(n, m->wave_max);
-    {  // bound the cross K/V cache to about half of the free HBM
+    const bool reuse = m->tr_cache && m->tr_cache->B == wave && m->tr_cache->T == T_cache &&
+                       m->tr_cache->cross_impl == m->cross_impl;  // same shape as last time: it fits
+    if (!reuse) {  // bound the cross K/V cache to about half of the free HBM (cudaMemGetInfo costs ~3 ms)
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         size_t per_chunk = ((size_t)m->L * 2 * T_cache + (m->cross_impl == 1 ? (size_t)m->S : (size_t)m->L * 2 * m->S)) *

@@ -109,7 +109,8 @@ struct Cache {
     int *tokens_out = nullptr, *out_len = nullptr, *cur_tok = nullptr, *done = nullptr, *scalars = nullptr;
     std::vector<Lane> lanes;
     std::vector<void *> owned;
-    int *pinned_scalars = nullptr;
+    int *pinned_scalars = nullptr;           // two snapshots of the lanes' step scalars (lagged EOT poll)
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaGraphExec_t graph_exec = nullptr;
 };
 

@@ -3,6 +3,7 @@
 //   cp.async.bulk into a shared-memory ring (the access pattern of cross_attn_absorbed_kernel).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bin/ubench_hbm tools/ubench_hbm.cu
 #include <cstdio>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,6 +49,41 @@ __global__ void __launch_bounds__(64) read_bulk(const uint8_t *__restrict__ p, s
                 const int s = g % STAGES;
                 ptx::mbar_wait(&full[s], (g / STAGES) & 1);
                 acc ^= *reinterpret_cast<volatile unsigned *>(buf + s * STAGE_BYTES);
+                ptx::mbar_arrive(&empty[s]);
+            }
+        if (acc == 0x12345678u) sink[0] = acc;
+    }
+}
+
+// the cross-attention's own pattern: per stage six 3-D tensor loads of [128 keys x 64 channels] boxes (128B swizzle)
+// out of a [B][1500][384] bf16 tensor, 2 stages of 96 KB
+__global__ void __launch_bounds__(64) read_tensor(const __grid_constant__ CUtensorMap map, int B, int nblk, unsigned *sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *buf = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int SB = 98304;
+    uint64_t *full = reinterpret_cast<uint64_t *>(buf + 2 * SB), *empty = full + 2;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int g = 0;
+        for (int b = blockIdx.x; b < B; b += gridDim.x)
+            for (int j = 0; j < nblk; j++, g++) {
+                const int s = g & 1;
+                ptx::mbar_wait(&empty[s], ((g >> 1) & 1) ^ 1);
+                ptx::mbar_expect_tx(&full[s], SB);
+                for (int a = 0; a < 6; a++) ptx::tma_load_3d(buf + s * SB + a * 16384, &map, &full[s], a * 64, j * 128, b);
+            }
+    } else if (threadIdx.x == 32) {
+        int g = 0;
+        unsigned acc = 0;
+        for (int b = blockIdx.x; b < B; b += gridDim.x)
+            for (int j = 0; j < nblk; j++, g++) {
+                const int s = g & 1;
+                ptx::mbar_wait(&full[s], (g >> 1) & 1);
+                acc ^= *reinterpret_cast<volatile unsigned *>(buf + s * SB);
                 ptx::mbar_arrive(&empty[s]);
             }
         if (acc == 0x12345678u) sink[0] = acc;
@@ -105,6 +141,28 @@ int main() {
         cudaFuncSetAttribute(read_bulk<ST, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST * SB + 512);
         float ms = time_ms([&] { read_bulk<ST, SB><<<296, 64, ST * SB + 512>>>(p, per, regions, sink); }, 5);
         printf("bulk ring 3 x 32 KB, 296 CTAs (2/SM): %.3f ms  %.0f GB/s\n", ms, (double)(per / SB) * SB * regions / ms / 1e6);
+    }
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
+        CUtensorMap map;
+        cuuint64_t dims[3] = {384, 1500, (cuuint64_t)regions}, str[2] = {768, 1500 * 768};
+        cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+        for (int promo = 0; promo < 2; promo++) {
+            CUresult r = ((EncodeFn)fp)(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B,
+                                        promo ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf("tensor map encode failed %d\n", (int)r); return 1; }
+            cudaFuncSetAttribute(read_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 98304 + 2048);
+            float ms = time_ms([&] { read_tensor<<<148, 64, 2 * 98304 + 2048>>>(map, regions, 12, sink); }, 5);
+            printf("tensor loads 6 x [128x64] per 96 KB stage, 2 stages, L2 promotion %s: %.3f ms  %.0f GB/s (valid bytes)\n",
+                   promo ? "256B" : "128B", ms, (double)per * regions / ms / 1e6);
+        }
     }
     return 0;
 }

@@ -21,6 +21,8 @@
 // under the other's exponentials.  Output: O / l in bf16, one 128-byte row segment per thread.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "sm100.cuh"
@@ -32,19 +34,34 @@ int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
 
 static constexpr int ATT_THREADS = 192;
 static constexpr int TILE_BYTES = 128 * 64 * 2;  // 128 rows x 64 bf16
-static constexpr int ATT_SMEM = 1024 + 6 * TILE_BYTES + 256;  // Q, K0, K1, V, P_lo, P_hi + barriers
+// KB = keys per block.  128: 96 KB of shared memory, 256 TMEM columns, 2 CTAs per SM.  64: 58 KB, 128 columns,
+// 3 CTAs per SM -- three softmax warps per SM sub-partition instead of two keep the MUFU pipe busier while
+// the other warps sit in their TMEM-load / max / P-store / barrier phases.
+template <int KB>
+struct AttCfg {
+    static constexpr int KV_BYTES = KB * 64 * 2;           // K or V tile
+    static constexpr int P_BYTES = (KB / 64) * TILE_BYTES;  // P: KB / 64 sub-tiles of [128 queries x 64 keys]
+    static constexpr int SMEM = 1024 + TILE_BYTES + 3 * KV_BYTES + P_BYTES + 256;  // Q, K0, K1, V, P + barriers
+    static constexpr int TMEM_COLS = 2 * KB;                // S: KB columns, O: 64 columns
+    static constexpr int MIN_CTAS = KB == 128 ? 2 : 3;
+};
 
 struct AttnTcParams {
-    CUtensorMap qkv_map;  // dims (3D, S, B), box (64, 128, 1)
+    CUtensorMap qkv_map;  // dims (3D, S, B), box (64, 128, 1): Q tiles
+    CUtensorMap kv_map;   // same tensor, box (64, KB, 1): K / V tiles
     __nv_bfloat16 *out;   // [B*S][D]
     int S, D, H, n_kblocks;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const __grid_constant__ AttnTcParams P) {
+template <int KB>
+__global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
+    encoder_attn_tc_kernel(const __grid_constant__ AttnTcParams P) {
+    using C = AttCfg<KB>;
+    constexpr int KV_BYTES = C::KV_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sQ = tiles, *sK = tiles + TILE_BYTES, *sV = tiles + 3 * TILE_BYTES, *sP = tiles + 4 * TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + 6 * TILE_BYTES);
+    uint8_t *sQ = tiles, *sK = tiles + TILE_BYTES, *sV = sK + 2 * KV_BYTES, *sP = sV + KV_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + C::P_BYTES);
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *s_full = bars + 6,
              *s_empty = bars + 7, *p_full = bars + 8, *pv_done = bars + 9;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 10);
@@ -55,6 +72,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
 
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&P.qkv_map);
+        ptx::prefetch_tmap(&P.kv_map);
         ptx::mbar_init(q_full, 1);
         for (int i = 0; i < 2; i++) ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
         ptx::mbar_init(v_full, 1);
@@ -65,14 +83,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
         ptx::fence_barrier_init();
     }
     if (warp == 5) {
-        ptx::tmem_alloc(tmem_holder, 256);
+        ptx::tmem_alloc(tmem_holder, C::TMEM_COLS);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+    const uint32_t tS = tmem_base, tO = tmem_base + KB;
 
     if (warp == 4) {
         // ===== TMA producer =====
@@ -82,21 +100,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
             auto load_k = [&](int j) {
                 const int s = j & 1;
                 ptx::mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
-                ptx::mbar_expect_tx(&k_full[s], TILE_BYTES);
-                ptx::tma_load_3d(sK + s * TILE_BYTES, &P.qkv_map, &k_full[s], P.D + h * 64, j * 128, b);
+                ptx::mbar_expect_tx(&k_full[s], KV_BYTES);
+                ptx::tma_load_3d(sK + s * KV_BYTES, &P.kv_map, &k_full[s], P.D + h * 64, j * KB, b);
             };
             load_k(0);
             for (int j = 0; j < nblk; j++) {
                 if (j + 1 < nblk) load_k(j + 1);  // K runs one block ahead of V
                 if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);  // V buffer is free once PV_{j-1} has completed
-                ptx::mbar_expect_tx(v_full, TILE_BYTES);
-                ptx::tma_load_3d(sV, &P.qkv_map, v_full, 2 * P.D + h * 64, j * 128, b);
+                ptx::mbar_expect_tx(v_full, KV_BYTES);
+                ptx::tma_load_3d(sV, &P.kv_map, v_full, 2 * P.D + h * 64, j * KB, b);
             }
         }
     } else if (warp == 5) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, KB, 0, 0);  // Q (K-major) x K (K-major)
             constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
             const uint64_t q_desc = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
             auto issue_s = [&](int j) {
@@ -104,7 +122,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
                 ptx::mbar_wait(&k_full[s], (j >> 1) & 1);
                 ptx::mbar_wait(s_empty, (j & 1) ^ 1);  // softmax has drained S_{j-1} from TMEM
                 ptx::tc_fence_after();
-                const uint64_t k_desc = ptx::umma_desc_sw128(ptx::smem_u32(sK + s * TILE_BYTES), 1, 64);
+                const uint64_t k_desc = ptx::umma_desc_sw128(ptx::smem_u32(sK + s * KV_BYTES), 1, 64);
 #pragma unroll
                 for (int k = 0; k < 4; k++) ptx::mma_bf16_ss(tS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
                 ptx::mma_commit(&k_empty[s]);
@@ -118,8 +136,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
                 ptx::mbar_wait(v_full, j & 1);
                 ptx::tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    // P: two 64-key sub-tiles, 32 B per 16-key step inside a sub-tile.
+                for (int k = 0; k < KB / 16; k++) {
+                    // P: 64-key sub-tiles, 32 B per 16-key step inside a sub-tile.
                     const uint64_t p_desc =
                         ptx::umma_desc_sw128(ptx::smem_u32(sP + (k >> 2) * TILE_BYTES), 1, 64) + 2 * (k & 3);
                     // V (MN-major): 16 keys = two 8-row groups of 1024 B.
@@ -141,29 +159,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
         uint8_t *p_row = sP + row * 128;
         const int sw = row & 7;
         for (int j = 0; j < nblk; j++) {
-            const int kvalid = min(128, P.S - j * 128);  // keys of this block inside the chunk
+            const int kvalid = min(KB, P.S - j * KB);  // keys of this block inside the chunk
             ptx::mbar_wait(s_full, j & 1);
             ptx::tc_fence_after();
-            // the whole 128-key score row into registers with one wait, then hand S back to the MMA warp
-            uint32_t v[128];
-            ptx::tmem_ld_32x32b_x32(tS + lane_addr, v);
-            ptx::tmem_ld_32x32b_x32(tS + lane_addr + 32, v + 32);
-            ptx::tmem_ld_32x32b_x32(tS + lane_addr + 64, v + 64);
-            ptx::tmem_ld_32x32b_x32(tS + lane_addr + 96, v + 96);
+            // the whole score row of the block into registers with one wait, then hand S back to the MMA warp
+            uint32_t v[KB];
+#pragma unroll
+            for (int cc = 0; cc < KB / 32; cc++) ptx::tmem_ld_32x32b_x32(tS + lane_addr + cc * 32, v + cc * 32);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 128; t++) asm volatile("" : "+r"(v[t]));  // no use of v[] may move above the wait
+            for (int t = 0; t < KB; t++) asm volatile("" : "+r"(v[t]));  // no use of v[] may move above the wait
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(s_empty);  // S_{j+1} = Q K_{j+1}^T runs under this block's exponentials
-            if (kvalid < 128) {
+            if (kvalid < KB) {
 #pragma unroll
-                for (int t = 0; t < 128; t++)
+                for (int t = 0; t < KB; t++)
                     if (t >= kvalid) v[t] = 0xff800000u;  // -inf: exp2 -> 0, never the maximum
             }
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int t = 0; t < 128; t += 4) {
+            for (int t = 0; t < KB; t += 4) {
                 mx0 = fmaxf(mx0, __uint_as_float(v[t])), mx1 = fmaxf(mx1, __uint_as_float(v[t + 1]));
                 mx2 = fmaxf(mx2, __uint_as_float(v[t + 2])), mx3 = fmaxf(mx3, __uint_as_float(v[t + 3]));
             }
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
             // p = exp2(s*c - m*c) -> bf16 pairs, in place over the score registers; row sum in fp32
             float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-            for (int t = 0; t < 128; t += 2) {
+            for (int t = 0; t < KB; t += 2) {
                 const float p0 = ptx::ex2(fmaf(__uint_as_float(v[t]), c, nmc));
                 const float p1 = ptx::ex2(fmaf(__uint_as_float(v[t + 1]), c, nmc));
                 l0 += p0, l1 += p1;
@@ -187,9 +203,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
             }
             l_run = l_run * alpha + (l0 + l1);
             if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O holds blocks < j
-            // P -> swizzled smem (K-major A operand): 128 keys = 2 sub-tiles x 8 chunks of 16 B
+            // P -> swizzled smem (K-major A operand): 64-key sub-tiles x 8 chunks of 16 B
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int i = 0; i < KB / 8; i++) {
                 uint8_t *dst = p_row + (i >> 3) * TILE_BYTES;
                 *reinterpret_cast<uint4 *>(dst + (((i & 7) ^ sw) << 4)) =
                     make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -239,8 +255,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) encoder_attn_tc_kernel(const _
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) ptx::tmem_dealloc(tmem_base, 256);
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
+
+template <int KB>
+static int launch_attn(cudaStream_t st, AttnTcParams &P, const __nv_bfloat16 *qkv, int B, int S, int H, int D) {
+    WB_CHECK(make_tmap_bf16(&P.kv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D, (uint64_t)S * 3 * D,
+                            KB, 3));
+    P.n_kblocks = cdiv(S, KB);
+    static bool opted = false;
+    if (!opted) {
+        WB_CUDA(cudaFuncSetAttribute(encoder_attn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<KB>::SMEM));
+        opted = true;
+    }
+    dim3 grid(cdiv(S, 128), H, B);
+    encoder_attn_tc_kernel<KB><<<grid, ATT_THREADS, AttCfg<KB>::SMEM, st>>>(P);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+int g_attn_kb = 128;  // keys per block of the encoder attention kernel (WB_ATTN_KB=64: 3-CTA/SM variant, measured equal)
 
 int encoder_attention_tc(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D) {
     if (B <= 0) return WB_OK;
@@ -248,16 +282,14 @@ int encoder_attention_tc(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat1
     AttnTcParams P;
     WB_CHECK(make_tmap_bf16(&P.qkv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D,
                             (uint64_t)S * 3 * D, 128, 3));
-    P.out = out, P.S = S, P.D = D, P.H = H, P.n_kblocks = cdiv(S, 128);
-    static bool opted = false;
-    if (!opted) {
-        WB_CUDA(cudaFuncSetAttribute(encoder_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        opted = true;
-    }
-    dim3 grid(cdiv(S, 128), H, B);
-    encoder_attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(P);
-    WB_LAUNCHED();
-    return WB_OK;
+    P.out = out, P.S = S, P.D = D, P.H = H;
+    static const bool env_once = [] {
+        const char *e = getenv("WB_ATTN_KB");
+        if (e) g_attn_kb = atoi(e) == 128 ? 128 : 64;
+        return true;
+    }();
+    (void)env_once;
+    return g_attn_kb == 128 ? launch_attn<128>(st, P, qkv, B, S, H, D) : launch_attn<64>(st, P, qkv, B, S, H, D);
 }
 
 }  // namespace wb

@@ -260,3 +260,31 @@ def test_small_shaped_config_runs_and_matches_oracle():
     ref, mg = om.greedy(enc_ref, margins=True)
     ok, msg = tokens_agree_up_to_margin(toks[0, :lens[0]], ref, mg, 2 * MARGIN_TAU)
     assert ok, msg
+
+
+def test_audio_ingest_feeds_the_batched_path(tmp_path):
+    """wav file (44.1 kHz stereo, 40 s) -> ingest -> two 30 s chunks -> tokens; equals the direct pcm call on the
+    ingested samples, and the second chunk equals a lone call (batch invariance through the ingest path)."""
+    import wave
+
+    from whisper_mojo_b200 import audio
+
+    cfg = WhisperConfig.tiny()
+    m, _ = build(cfg)
+    sr = 44100
+    t = np.arange(sr * 40) / sr
+    rng_ = np.random.default_rng(11)
+    x = 0.3 * np.sin(2 * np.pi * (200 + 20 * t) * t) + 0.05 * rng_.standard_normal(len(t))
+    st = np.stack([x, 0.5 * x], axis=1)
+    p = str(tmp_path / "clip.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(2), w.setsampwidth(2), w.setframerate(sr)
+        w.writeframes((np.clip(st, -1, 1) * 32767).astype(np.int16).tobytes())
+    data, sr2 = audio.load_wav(p)
+    ids = audio.transcribe_audio(m, data, sr2)
+    assert len(ids) == 2 and all(len(i) == cfg.max_tokens for i in ids)
+    pcm = audio.chunk_audio(audio.prepare_audio(data, sr2))
+    toks, lens = m.transcribe_pcm_batch(pcm)
+    assert [list(toks[i, :lens[i]]) for i in range(2)] == ids
+    t1, l1 = m.transcribe_pcm_batch(pcm[1:])
+    assert list(t1[0, :l1[0]]) == ids[1]

@@ -13,3 +13,4 @@ from .tokenizer import Tokenizer  # noqa: F401
 from .whisper_tensor import Tensor  # noqa: F401
 from .layers import KVCache, LayerCache, MultiHeadAttention, ResidualAttentionBlock  # noqa: F401
 from .whisper import DeviceKVCache, Whisper, WhisperDecoder, WhisperEncoder  # noqa: F401
+from . import audio, export  # noqa: F401,E402  (host-side ingest and checkpoint export)

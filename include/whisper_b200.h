@@ -178,8 +178,10 @@ int wm_teacher_forced(wm_model m, const float *enc_out_dev, int n_chunks, const 
 /* Phase timers of the last wm_transcribe* call, CUDA-event milliseconds on the model's stream:
  * [0] frontend, [1] encoder, [2] cross-KV projection, [3] prefill + decode loop, [4] total. */
 int wm_last_timing(wm_model m, float ms[5]);
-/* Device-time of the dominant decode kernel (cross-attention) accumulated over the last
- * wm_transcribe* call: total milliseconds and launch count (roofline evidence for bench.py). */
+/* Device-time of decode-step kernels accumulated over the last wm_transcribe* call (CUDA events around each
+ * launch; roofline evidence for bench.py): total milliseconds and launch count of category `kernel` --
+ * "cross_attention" (option profile_attn >= 1), and with profile_attn = 2 also "self_attention", "gemm_qkv",
+ * "gemm_o", "gemm_cross_q", "gemm_cross_o", "gemm_fc1", "gemm_fc2", "layer_norm", "gemm_logits", "misc". */
 int wm_last_kernel_timing(wm_model m, const char *kernel, float *total_ms, int64_t *launches);
 
 /* ------------------------------------------------------------------------------------------ */

@@ -13,6 +13,7 @@ import pytest
 import torch
 
 from gpu_util import tokens_agree_up_to_margin
+from oracle import logmel_oracle as LM
 from oracle import oracle as O
 from whisper_mojo_b200 import DeviceKVCache, Tensor, WeightLoader, Whisper, WhisperConfig, _lib, synth
 
@@ -288,3 +289,44 @@ def test_audio_ingest_feeds_the_batched_path(tmp_path):
     assert [list(toks[i, :lens[i]]) for i in range(2)] == ids
     t1, l1 = m.transcribe_pcm_batch(pcm[1:])
     assert list(t1[0, :l1[0]]) == ids[1]
+
+
+def test_config3_encoder_batch_256_full_size():
+    """BASELINE.json configs[2]: encoder-only forward of 256 synthetic log-mel chunks (two 128-chunk sub-batches
+    through the CTA-pair GEMMs / TMA-store epilogues at their real sizes).  The oracle is slow, so 4 chunks spread
+    over the batch are checked against it; every chunk must equal its own solo encode
+    (size-independent property: batch invariance) and be finite."""
+    import torch
+
+    cfg = WhisperConfig.tiny()
+    m, w = build(cfg)
+    n = 256
+    mel = synth.make_mel(8, cfg, 5)
+    mel = np.concatenate([mel] * (n // 8))  # 256 chunks, 8 distinct
+    mel[129] = mel[129][:, ::-1]  # one chunk unlike any other in the second sub-batch
+    enc = m.encode(mel)
+    assert enc.shape == (n, cfg.n_audio_ctx, cfg.d_model) and np.isfinite(enc).all()
+    om = O.OracleWhisper(cfg, w)
+    for i in (0, 127, 129, 255):
+        err = np.abs(enc[i] - om.encode(mel[i]))
+        assert err.max() <= ENC_MAX and err.mean() <= ENC_MEAN, (i, err.max(), err.mean())
+    for i in range(8, n):
+        if i != 129:
+            assert np.array_equal(enc[i], enc[i % 8]), i  # same input, other batch position -> identical bits
+    assert np.array_equal(m.encode(mel[129:130])[0], enc[129])
+
+
+def test_config2_frontend_one_hour_of_audio():
+    """BASELINE.json configs[1]: 1 h of synthetic 16 kHz audio (120 chunks) through the log-mel frontend on one GPU;
+    parity on a sample of chunks against the numpy oracle (1e-4 of the range), every chunk finite and clamped to
+    the 8-decade window (size-independent property of the recipe: max - min <= 2.0 after (x + 4) / 4)."""
+    cfg = WhisperConfig.tiny()
+    m = Whisper(cfg)
+    a = synth.make_audio(120, seed=9)
+    mel = m.log_mel(a)
+    assert mel.shape == (120, 80, 3000) and np.isfinite(mel).all()
+    spread = mel.reshape(120, -1).max(axis=1) - mel.reshape(120, -1).min(axis=1)
+    assert (spread <= 2.0 + 1e-5).all()
+    for i in (0, 59, 119):
+        ref = LM.log_mel(a[i])
+        assert np.abs(mel[i] - ref).max() / (ref.max() - ref.min()) <= 1e-4, i

@@ -580,10 +580,17 @@ int wm_last_timing(wm_model h, float ms[5]) {
 
 int wm_last_kernel_timing(wm_model h, const char *kernel, float *total_ms, int64_t *launches) {
     MODEL(m, h);
-    WB_ARG(kernel && !strcmp(kernel, "cross_attention"), "only \"cross_attention\" is instrumented");
-    if (total_ms) *total_ms = m->cross_timer.total_ms;
-    if (launches) *launches = m->cross_timer.launches;
-    return WB_OK;
+    static const char *names[TK_COUNT] = {"cross_attention", "self_attention", "gemm_qkv", "gemm_o", "gemm_cross_q",
+                                          "gemm_cross_o", "gemm_fc1", "gemm_fc2", "layer_norm", "gemm_logits", "misc"};
+    WB_ARG(kernel, "null kernel name");
+    for (int k = 0; k < TK_COUNT; k++)
+        if (!strcmp(kernel, names[k])) {
+            if (total_ms) *total_ms = m->cross_timer.total_ms[k];
+            if (launches) *launches = m->cross_timer.launches[k];
+            return WB_OK;
+        }
+    set_error("unknown kernel category %s (cross_attention is timed with profile_attn=1, all of them with 2)", kernel);
+    return WB_ERR_ARG;
 }
 
 

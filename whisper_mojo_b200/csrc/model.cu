@@ -454,31 +454,18 @@ int cache_set_encoder(Cache *c, const float *enc_out_dev) {
 }
 
 template <typename Fn>
-static int timed_kernel(Model *m, cudaStream_t st, Fn launch) {
-    if (!m->profile_attn) return launch();
+static int timed_kernel(Model *m, cudaStream_t st, int category, Fn launch) {
+    if (!(m->profile_attn == 2 || (m->profile_attn == 1 && category == TK_CROSS))) return launch();
     KernelTimer &t = m->cross_timer;
     while ((int)t.ev.size() < t.used + 2) {
         cudaEvent_t e;
         WB_CUDA(cudaEventCreate(&e));
         t.ev.push_back(e);
     }
+    if ((int)t.cat.size() < t.used / 2 + 1) t.cat.resize(t.used / 2 + 1);
+    t.cat[t.used / 2] = category;
     WB_CUDA(cudaEventRecord(t.ev[t.used], st));
     int rc = launch();
-    WB_CUDA(cudaEventRecord(t.ev[t.used + 1], st));
-    t.used += 2;
-    return rc;
-}
-
-static int timed_cross_attention(Model *m, cudaStream_t st, const DecodeAttnArgs &a) {
-    if (!m->profile_attn) return decode_attention(st, a);
-    KernelTimer &t = m->cross_timer;
-    while ((int)t.ev.size() < t.used + 2) {
-        cudaEvent_t e;
-        WB_CUDA(cudaEventCreate(&e));
-        t.ev.push_back(e);
-    }
-    WB_CUDA(cudaEventRecord(t.ev[t.used], st));
-    int rc = decode_attention(st, a);
     WB_CUDA(cudaEventRecord(t.ev[t.used + 1], st));
     t.used += 2;
     return rc;
@@ -494,58 +481,78 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     // cache-wide segment sizes; this lane's chunks start b_off rows into every segment
     const size_t self_seg = (size_t)c->B * c->T * D, cross_seg = (size_t)c->B * m->S * D;
     const size_t self_off = (size_t)ln.b_off * c->T * D, cross_off = (size_t)ln.b_off * m->S * D;
-    WB_CHECK(embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, ln.g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
-                      m->dec[0].ln1_b, ln.x, ln.xn));
+    WB_CHECK(timed_kernel(m, st, TK_LN, [&] {
+        return embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, ln.g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
+                        m->dec[0].ln1_b, ln.x, ln.xn);
+    }));
     for (int l = 0; l < m->L; l++) {
         const LayerDev &d = m->dec[l];
         bf16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
         bf16 *ck = c->cross_kv ? c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off : nullptr;
         bf16 *cv = ck ? ck + cross_seg : nullptr;
-        if (l > 0) WB_CHECK(ln_bf16(st, ln.x, d.ln1_g, d.ln1_b, B, D, ln.xn, nullptr));
+        if (l > 0) WB_CHECK(timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, d.ln1_g, d.ln1_b, B, D, ln.xn, nullptr); }));
         {  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
             GemmDesc g = plain_gemm(ln.xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, ln.q, D);
             g.n_seg_ptrs = 3, g.seg_cols = D;
             g.out[1] = sk, g.out_ld[1] = (int64_t)c->T * D, g.dyn_mult[1] = D;
             g.out[2] = sv, g.out_ld[2] = (int64_t)c->T * D, g.dyn_mult[2] = D;
             g.dyn_off = cur_len;
-            WB_CHECK(gemm_run(st, g, impl));
+            WB_CHECK(timed_kernel(m, st, TK_QKV, [&] { return gemm_run(st, g, impl); }));
         }
         DecodeAttnArgs a;
         a.q = ln.q, a.K = sk, a.V = sv, a.out = ln.attn, a.kv_batch_stride = (int64_t)c->T * D;
         a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
         a.splits = 1, a.ws = nullptr;
-        WB_CHECK(decode_attention(st, a));
-        WB_CHECK(gemm_run(st, plain_gemm(ln.attn, B, D, d.wo, D, d.bo, EPI_RESID_F32, ln.x, D), impl));
+        WB_CHECK(timed_kernel(m, st, TK_SELF, [&] { return decode_attention(st, a); }));
+        WB_CHECK(timed_kernel(m, st, TK_O, [&] {
+            return gemm_run(st, plain_gemm(ln.attn, B, D, d.wo, D, d.bo, EPI_RESID_F32, ln.x, D), impl);
+        }));
         // cross attention over the encoder positions (layers.mojo:463-488)
-        WB_CHECK(ln_bf16(st, ln.x, d.ln2_g, d.ln2_b, B, D, ln.xn, nullptr));
+        WB_CHECK(timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, d.ln2_g, d.ln2_b, B, D, ln.xn, nullptr); }));
         if (c->cross_impl == 1) {
             // absorbed form: q' = (Wk_h^T Wq_h) x + ..., attend over enc_out, out = (Wo Wv_h) ctx_h + ...
             const int HD = m->H * D;
-            WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.wqk, HD, d.bqk, EPI_STORE_BF16, ln.qp, HD), impl));
+            WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
+                return gemm_run(st, plain_gemm(ln.xn, B, D, d.wqk, HD, d.bqk, EPI_STORE_BF16, ln.qp, HD), impl);
+            }));
             const bf16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
-            WB_CHECK(timed_kernel(m, st, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
-            WB_CHECK(gemm_run(st, plain_gemm(ln.ctx, B, HD, d.wov, D, d.bov, EPI_RESID_F32, ln.x, D), impl));
+            WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
+            WB_CHECK(timed_kernel(m, st, TK_CO, [&] {
+                return gemm_run(st, plain_gemm(ln.ctx, B, HD, d.wov, D, d.bov, EPI_RESID_F32, ln.x, D), impl);
+            }));
         } else {
-            WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, ln.q, D), impl));
+            WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
+                return gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, ln.q, D), impl);
+            }));
             a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;
             a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
             a.splits = ln.cross_splits, a.ws = ln.attn_ws;
-            WB_CHECK(timed_cross_attention(m, st, a));
-            WB_CHECK(gemm_run(st, plain_gemm(ln.attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, ln.x, D), impl));
+            WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return decode_attention(st, a); }));
+            WB_CHECK(timed_kernel(m, st, TK_CO, [&] {
+                return gemm_run(st, plain_gemm(ln.attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, ln.x, D), impl);
+            }));
         }
         // MLP (layers.mojo:490-517)
-        WB_CHECK(ln_bf16(st, ln.x, d.ln3_g, d.ln3_b, B, D, ln.xn, nullptr));
-        WB_CHECK(gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, ln.h, m->F), impl));
-        WB_CHECK(gemm_run(st, plain_gemm(ln.h, B, m->F, d.w2, D, d.b2, EPI_RESID_F32, ln.x, D), impl));
+        WB_CHECK(timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, d.ln3_g, d.ln3_b, B, D, ln.xn, nullptr); }));
+        WB_CHECK(timed_kernel(m, st, TK_FC1, [&] {
+            return gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, ln.h, m->F), impl);
+        }));
+        WB_CHECK(timed_kernel(m, st, TK_FC2, [&] {
+            return gemm_run(st, plain_gemm(ln.h, B, m->F, d.w2, D, d.b2, EPI_RESID_F32, ln.x, D), impl);
+        }));
     }
     if (with_logits) {  // whisper.mojo:156-166 + argmax :198,219
-        WB_CHECK(ln_bf16(st, ln.x, W + m->lay.dec_ln_w, W + m->lay.dec_ln_b, B, D, ln.xn, nullptr));
+        WB_CHECK(timed_kernel(m, st, TK_LN, [&] {
+            return ln_bf16(st, ln.x, W + m->lay.dec_ln_w, W + m->lay.dec_ln_b, B, D, ln.xn, nullptr);
+        }));
         GemmDesc g = plain_gemm(ln.xn, B, D, m->tok_emb_bf16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
         g.part_val = ln.part_val, g.part_idx = ln.part_idx;
         g.logits = (store_logits || impl == GEMM_IMPL_REF) ? ln.logits : nullptr;
         WB_ARG(!(store_logits || impl == GEMM_IMPL_REF) || ln.logits, "decode_step: cache has no logits buffer");
-        WB_CHECK(gemm_run(st, g, impl));
-        WB_CHECK(argmax_partials(st, ln.part_val, ln.part_idx, B, gemm_tiles_n(m->V), ln.next));
+        WB_CHECK(timed_kernel(m, st, TK_LOGITS, [&] { return gemm_run(st, g, impl); }));
+        WB_CHECK(timed_kernel(m, st, TK_MISC, [&] {
+            return argmax_partials(st, ln.part_val, ln.part_idx, B, gemm_tiles_n(m->V), ln.next);
+        }));
     }
     return WB_OK;
 }
@@ -750,10 +757,11 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
         m->timing[0] = acc[0], m->timing[1] = acc[1], m->timing[2] = 0.f, m->timing[3] = acc[2];
         m->timing[4] = acc[0] + acc[1] + acc[2];
         KernelTimer &t = m->cross_timer;
-        t.total_ms = 0.f, t.launches = 0;
+        for (int k = 0; k < TK_COUNT; k++) t.total_ms[k] = 0.f, t.launches[k] = 0;
         for (int i = 0; i + 1 < t.used; i += 2) {
             float ems = 0.f;
-            if (cudaEventElapsedTime(&ems, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.total_ms += ems, t.launches++;
+            if (cudaEventElapsedTime(&ems, t.ev[i], t.ev[i + 1]) == cudaSuccess)
+                t.total_ms[t.cat[i / 2]] += ems, t.launches[t.cat[i / 2]]++;
         }
     }
     return rc;

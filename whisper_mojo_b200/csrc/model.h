@@ -42,11 +42,15 @@ struct LayerDev {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;  // attn_ln, cross_ln (dec), mlp_ln
 };
 
+// Event pairs around individual decode-step launches (option "profile_attn": 1 = cross-attention only, the
+// bench's roofline pass; 2 = every kernel of the step, by category).
+enum TimedKernel { TK_CROSS = 0, TK_SELF, TK_QKV, TK_O, TK_CQ, TK_CO, TK_FC1, TK_FC2, TK_LN, TK_LOGITS, TK_MISC, TK_COUNT };
 struct KernelTimer {
     std::vector<cudaEvent_t> ev;
+    std::vector<int> cat;  // category of event pair i
     int used = 0;
-    float total_ms = 0.f;
-    int64_t launches = 0;
+    float total_ms[TK_COUNT] = {};
+    int64_t launches[TK_COUNT] = {};
 };
 
 struct Model {

@@ -299,7 +299,11 @@ class Whisper:
         _lib.check(_lib.load().wm_last_timing(self._h, ms))
         return dict(zip(("frontend_ms", "encoder_ms", "cross_kv_ms", "decode_ms", "total_ms"), [float(x) for x in ms]))
 
-    def last_cross_attention_timing(self):
+    def last_kernel_timing(self, kernel: str = "cross_attention"):
+        """(total ms, launches) of one decode-kernel category of the last transcribe call (profile_attn option)."""
         ms, n = c_float(0), c_int64(0)
-        _lib.check(_lib.load().wm_last_kernel_timing(self._h, b"cross_attention", ctypes.byref(ms), ctypes.byref(n)))
+        _lib.check(_lib.load().wm_last_kernel_timing(self._h, kernel.encode(), ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
+
+    def last_cross_attention_timing(self):
+        return self.last_kernel_timing("cross_attention")

@@ -80,6 +80,23 @@ def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
     assert np.abs(debug_gemm(3, A, W, b, 1) - g).max() <= 2e-2
     x0 = rng.standard_normal((M, N), dtype=np.float32)
     assert np.abs(debug_gemm(3, A, W, b, 2, out0=x0) - (x0 + ref)).max() <= tol
+    lg = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
+    am = debug_gemm(3, A, W, None, 4)  # fused logits + argmax partials (first maximum wins)
+    assert np.array_equal(am[:, -1].astype(np.int64), lg.argmax(1))
+    assert np.abs(am[:, :-1] - lg[:, :-1]).max() <= tol
+
+
+def test_gemm_cta_pair_argmax_ties_and_vocab_width():
+    A = np.zeros((3, 64), np.float32)
+    A[:, 0] = 1.0
+    W = np.zeros((700, 64), np.float32)
+    W[[5, 300, 650], 0] = 2.0  # equal maxima in three different tiles
+    W[[130, 131], 0] = 2.0
+    assert np.all(debug_gemm(3, A, W, None, 4)[:, -1] == 5)
+    A = rng.standard_normal((300, 384), dtype=np.float32)
+    W = rng.standard_normal((51865 // 8, 384), dtype=np.float32) / 20  # ragged last tile like the real vocabulary
+    lg = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
+    assert np.array_equal(debug_gemm(3, A, W, None, 4)[:, -1].astype(np.int64), lg.argmax(1))
 
 
 @pytest.mark.parametrize("cs,Cin,L,N,B", [(1, 128, 300, 128, 2), (2, 128, 301, 256, 3), (2, 384, 3000, 384, 2), (1, 128, 3000, 384, 3)])

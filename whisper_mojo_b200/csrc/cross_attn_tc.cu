@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
     // its 8 MMAs are done, so the refill of the stage starts ~0.7 us before the block's last MMA retires
     uint64_t *enc_full = bars, *enc_empty = bars + 2 * XA_MAX_ATOMS, *q_full = enc_empty + XA_MAX_ATOMS, *q_empty = q_full + 1,
              *s_full = q_empty + 1, *s_empty = s_full + 2, *p_full = s_empty + 2, *c_done = p_full + 1,
-             *c_empty = c_done + 1;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(c_empty + 1);
-    float *s_red = reinterpret_cast<float *>(c_empty + 2);  // [4 warps][16] cross-warp reduction scratch
+             *c_empty = c_done + 1;  // c_empty[2]: the context accumulator is double buffered over chunks
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(c_empty + 2);
+    float *s_red = reinterpret_cast<float *>(c_empty + 3);  // [4 warps][16] cross-warp reduction scratch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = P.n_blocks, D = P.D;
@@ -107,18 +107,20 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         ptx::mbar_init(q_empty, 1);
         ptx::mbar_init(p_full, 4);
         ptx::mbar_init(c_done, 1);
-        ptx::mbar_init(c_empty, 4);
+        ptx::mbar_init(&c_empty[0], 4);
+        ptx::mbar_init(&c_empty[1], 4);
         ptx::fence_barrier_init();
     }
     if (warp == 5) {
-        ptx::tmem_alloc(tmem_holder, 256);
+        ptx::tmem_alloc(tmem_holder, 512);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    // TMEM columns: score partials S[stage][part] @ 16 * (stage * n_acc + part) (< 96), context C_m @ 128 + 32 m.
+    // TMEM columns: score partials S[stage][part] @ 16 * (stage * n_acc + part) (< 96), context C_m of chunk parity
+    // p @ 128 + 128 p + 32 m (two context buffers: the epilogue of chunk i runs under the first block of chunk i+1).
     // Back-to-back MMAs into one accumulator serialise (~45 ns each), so the K = D reduction of the scores is
     // split into one partial accumulator per atom pair and the issue order interleaves accumulators.
     const uint32_t tS0 = tmem_base, tC0 = tmem_base + 128;
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
             const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sP), 1, 64);
             int g = 0, ci = 0;
             for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
-                ptx::mbar_wait(c_empty, (ci & 1) ^ 1);  // epilogue of the previous chunk has drained C
+                ptx::mbar_wait(&c_empty[ci & 1], ((ci >> 1) & 1) ^ 1);  // epilogue of chunk ci - 2 has drained this buffer
+                const uint32_t tC = tC0 + (ci & 1) * 128;
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
                     ptx::mbar_wait(p_full, g & 1);  // softmax(g) done => scores(g) done reading the stage too
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                     for (int m = 0; m < n_acc; m++) {  // atom pair m = channels [128 m, 128 m + 128)
 #pragma unroll
                         for (int k = 0; k < 8; k++)
-                            ptx::mma_bf16_ss(tC0 + 32 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
+                            ptx::mma_bf16_ss(tC + 32 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
                                              p_desc0 + (k >> 2) * (QATOM_BYTES >> 4) + 2 * (k & 3), idesc_c, (j | k) != 0);
                         ptx::mma_commit(&enc_empty[s * (XA_MAX_ATOMS / 2) + m]);
                     }
@@ -210,9 +213,43 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         for (int i = row; i < 2 * QATOM_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0, 0, 0, 0);
         ptx::fence_proxy_async_smem();
         named_bar_sync(2, 128);
-        int g = 0, ci = 0;
+        // chunk epilogue: l[h] = sum over the 128 threads; ctx = C / l.  Deferred: it runs after the softmax of the
+        // NEXT chunk's first block (its context MMAs are long done by then), so the softmax warps never wait on c_done
+        auto epilogue = [&](int b_out, float *l_sum, uint32_t tC) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int h = 0; h < H; h++) l_sum[h] += __shfl_xor_sync(0xffffffffu, l_sum[h], o);
+            }
+            if (lane < H) {
+                float v = l_sum[0];
+#pragma unroll
+                for (int h = 1; h < H; h++)
+                    if (lane == h) v = l_sum[h];
+                s_red[warp * 16 + lane] = v;
+            }
+            named_bar_sync(1, 128);
+            float inv[H];
+#pragma unroll
+            for (int h = 0; h < H; h++) inv[h] = 1.0f / (s_red[h] + s_red[16 + h] + s_red[32 + h] + s_red[48 + h]);
+            ptx::tc_fence_after();
+            __nv_bfloat16 *dst = P.ctx + (size_t)b_out * H * D;
+            for (int m = 0; m < n_acc; m++) {
+                uint32_t cv[16];
+                tmem_ld_32x32b_x16(tC + 32 * m + lane_addr, cv);
+                ptx::tmem_ld_wait();
+                const int c = m * 128 + row;
+#pragma unroll
+                for (int h = 0; h < H; h++) dst[(size_t)h * D + c] = __float2bfloat16(__uint_as_float(cv[h]) * inv[h]);
+            }
+            ptx::tc_fence_before();
+            named_bar_sync(2, 128);  // s_red reads are done; C buffer drained by all four warps
+        };
+        int g = 0, ci = 0, b_prev = -1;
+        float l_prev[H];
         for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
             float m_run[H], l_part[H];
+            const uint32_t tC = tC0 + (ci & 1) * 128;
 #pragma unroll
             for (int h = 0; h < H; h++) m_run[h] = -INFINITY, l_part[h] = 0.f;
             for (int j = 0; j < nblk; j++, g++) {
@@ -286,11 +323,11 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 if (j > 0 && moved) {
                     for (int m = 0; m < n_acc; m++) {
                         uint32_t cv[16];
-                        tmem_ld_32x32b_x16(tC0 + 32 * m + lane_addr, cv);
+                        tmem_ld_32x32b_x16(tC + 32 * m + lane_addr, cv);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int h = 0; h < H; h++) cv[h] = __float_as_uint(__uint_as_float(cv[h]) * alpha[h]);
-                        tmem_st_32x32b_x16(tC0 + 32 * m + lane_addr, cv);
+                        tmem_st_32x32b_x16(tC + 32 * m + lane_addr, cv);
                     }
                     ptx::tmem_st_wait();
                 }
@@ -300,49 +337,31 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 named_bar_sync(2, 128);  // all four warps are past their s_red reads before the next block writes it
                 if (lane == 0) ptx::mbar_arrive(p_full);
                 if (threadIdx.x == 0) XA_STAMP(2, g, 3);
+                if (j == 0 && b_prev >= 0) {  // previous chunk: its last context MMA completed before this block's P store
+                    epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * 128);
+                    if (lane == 0) ptx::mbar_arrive(&c_empty[(ci - 1) & 1]);
+                    b_prev = -1;
+                }
             }
-            // ---- chunk epilogue: l[h] = sum over the 128 threads; ctx = C / l ----
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int h = 0; h < H; h++) l_part[h] += __shfl_xor_sync(0xffffffffu, l_part[h], o);
-            }
-            if (lane < H) {
-                float v = l_part[0];
-#pragma unroll
-                for (int h = 1; h < H; h++)
-                    if (lane == h) v = l_part[h];
-                s_red[warp * 16 + lane] = v;
-            }
-            named_bar_sync(1, 128);
-            float inv[H];
-#pragma unroll
-            for (int h = 0; h < H; h++) inv[h] = 1.0f / (s_red[h] + s_red[16 + h] + s_red[32 + h] + s_red[48 + h]);
+            for (int h = 0; h < H; h++) l_prev[h] = l_part[h];
+            b_prev = b;
+        }
+        if (b_prev >= 0) {  // last chunk of this CTA
             ptx::mbar_wait(c_done, (g - 1) & 1);
-            ptx::tc_fence_after();
-            __nv_bfloat16 *dst = P.ctx + (size_t)b * H * D;
-            for (int m = 0; m < n_acc; m++) {
-                uint32_t cv[16];
-                tmem_ld_32x32b_x16(tC0 + 32 * m + lane_addr, cv);
-                ptx::tmem_ld_wait();
-                const int c = m * 128 + row;
-#pragma unroll
-                for (int h = 0; h < H; h++) dst[(size_t)h * D + c] = __float2bfloat16(__uint_as_float(cv[h]) * inv[h]);
-            }
-            ptx::tc_fence_before();
-            named_bar_sync(2, 128);
-            if (lane == 0) ptx::mbar_arrive(c_empty);
+            epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * 128);
+            if (lane == 0) ptx::mbar_arrive(&c_empty[(ci - 1) & 1]);
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) ptx::tmem_dealloc(tmem_base, 256);
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 size_t cross_attn_absorbed_smem(int D) {
     const int atoms = D / 64;
     return 1024 + (size_t)2 * atoms * ATOM_BYTES + XA_MAX_ATOMS * QATOM_BYTES + 2 * QATOM_BYTES +
-           (3 * XA_MAX_ATOMS + 12) * 8 + 64 * 4 + 64;
+           (3 * XA_MAX_ATOMS + 13) * 8 + 64 * 4 + 64;
 }
 
 bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 384 && H <= 16; }

@@ -618,6 +618,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                     out_ctr++;
                 } else {
                     epi_finish<EPI>(p, b, m, n_first + c * 32, v[c & 1], e[c & 1], sbias + c * 32, best, best_idx);
+                    if (EPI == EPI_ARGMAX && (c & 1)) {
+                        // one (max, first index) partial per 64 columns, the slot layout of the single-CTA kernel
+                        if (m < p.rows_per_batch) {
+                            const long long grow = (long long)b * p.rows_per_batch + m;
+                            const long long slot = grow * p.tiles_n * PART_PER_TILE + (n_first + (c - 1) * 32) / 64;
+                            p.part_val[slot] = best;
+                            p.part_idx[slot] = best_idx;
+                        }
+                        best = -INFINITY, best_idx = 0x7fffffff;
+                    }
                 }
             }
         }
@@ -825,14 +835,18 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
         return true;
     }();
     (void)env_once;
-    // CTA-pair kernel for the large GEMMs (encoder, cross-K/V): at least one full wave of 256-row pair tiles.
     const int pair_tiles_m = cdiv(d.rows_per_batch, 256);
-    const bool pair_ok = d.epi != EPI_ARGMAX;
+    const bool pair_ok = true;
+    // CTA-pair kernel: always for a full wave of pair tiles; for the decode-step GEMMs (M = batch <= 2048) already
+    // from 12 pair tiles on (measured: 10-15 % faster than 48..288 single-CTA tiles) unless the output goes through
+    // the device-side KV-cache offset (per-thread stores, where the single-CTA kernel wins).
+    const int64_t pair_tiles = (int64_t)d.batches * pair_tiles_m * cdiv(d.N, 256);
     const bool want_pair = impl == GEMM_IMPL_TC_PAIR ||
-                           (impl == GEMM_IMPL_TC && (int64_t)d.batches * pair_tiles_m * cdiv(d.N, 256) >= sms / 2);
+                           (impl == GEMM_IMPL_TC && (pair_tiles >= sms / 2 || (pair_tiles >= 12 && !d.dyn_off)));
     if (pair_ok && want_pair) {
         GemmPairParams Q;
-        const int bn2 = pick_pair_bn(d.N);  // output routing is per 32-column chunk, so any tile width works
+        // output routing is per 32-column chunk, so any tile width works; the argmax partials need 64-column pairs
+        const int bn2 = d.epi == EPI_ARGMAX ? 256 : pick_pair_bn(d.N);
         for (int t = 0; t < 3; t++) Q.a_map[t] = P.a_map[t];
         WB_CHECK(make_tmap_bf16(&Q.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, bn2 / 2, 2));
         Q.d = p;
@@ -863,6 +877,7 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
                 if (d.epi == EPI_GELU_BF16) return launch_pair_bn<EPI_GELU_BF16>(st, Q, grid, bn2);
                 return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
             }
+            case EPI_ARGMAX: return launch_pair<EPI_ARGMAX, 256, false>(st, Q, grid);
             case EPI_STORE_F32: return launch_pair_bn<EPI_STORE_F32>(st, Q, grid, bn2);
             case EPI_GELU_POS_F32: return launch_pair_bn<EPI_GELU_POS_F32>(st, Q, grid, bn2);
         }

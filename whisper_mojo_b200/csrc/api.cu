@@ -15,6 +15,7 @@
 namespace wb {
 
 std::atomic<int64_t> g_launches{0};
+bool g_pdl = false;  // programmatic dependent launch of the decode-step kernels: measured, no gain
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -383,6 +384,13 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     if (!strcmp(key, "gemm_impl")) m->gemm_impl = (int)value;
     else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
     else if (!strcmp(key, "frontend_impl")) m->frontend_impl = (int)value;
+    else if (!strcmp(key, "pdl")) {  // process-wide; captured decode graphs keep the setting they were built with
+        g_pdl = value != 0;
+        if (m->tr_cache) {
+            cache_destroy(m->tr_cache);
+            m->tr_cache = nullptr;
+        }
+    }
     else if (!strcmp(key, "use_graph")) m->use_graph = (int)value;
     else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
     else if (!strcmp(key, "cross_impl")) {

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = P.n_blocks, D = P.D;
+    pdl_launch_dependents();
     constexpr int H = ATOMS;  // head_dim = 64, so H = D / 64 = number of 64-channel atoms
     constexpr int n_acc = ATOMS / 2;  // C accumulators of [128 channels x 16 heads]
 
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
     // Back-to-back MMAs into one accumulator serialise (~45 ns each), so the K = D reduction of the scores is
     // split into one partial accumulator per atom pair and the issue order interleaves accumulators.
     const uint32_t tS0 = tmem_base, tC0 = tmem_base + 128;
+    pdl_wait();  // the prologue above overlapped the previous kernel (programmatic dependent launch)
 
     if (warp == 4) {
         // ===== TMA producer =====
@@ -391,7 +393,7 @@ int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __n
             WB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             opted[slot] = true;
         }
-        kernel<<<grid, XA_THREADS, smem, st>>>(P);
+        WB_CUDA(launch_pdl(kernel, dim3(grid), dim3(XA_THREADS), smem, st, P));
         WB_LAUNCHED();
         return WB_OK;
     };

@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.batches * p.tiles_m_per_batch * p.tiles_n;
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         for (int t = 0; t < p.taps; t++) ptx::prefetch_tmap(&P.a_map[t]);
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();  // everything above overlapped the previous kernel; operands / outputs are touched from here on
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -465,6 +467,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const uint32_t rank = ptx::cluster_ctarank();
     const int total_tiles = p.batches * P.pair_tiles_m_per_batch * P.pair_tiles_n;
     const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         for (int t = 0; t < p.taps; t++) ptx::prefetch_tmap(&P.a_map[t]);
@@ -488,6 +491,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer (one per CTA) =====
@@ -724,7 +728,7 @@ static int launch_tc(cudaStream_t st, const GemmTcParams &P, int grid) {
         WB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
-    gemm_tc_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
+    WB_CUDA(launch_pdl(gemm_tc_kernel<EPI>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, P));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -737,7 +741,7 @@ static int launch_pair(cudaStream_t st, const GemmPairParams &P, int grid) {
         WB_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BN2, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    gemm_pair_kernel<EPI, BN2, TMA_OUT><<<grid, TC_THREADS, smem, st>>>(P);
+    WB_CUDA(launch_pdl(gemm_pair_kernel<EPI, BN2, TMA_OUT>, dim3(grid), dim3(TC_THREADS), smem, st, P));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -902,6 +906,8 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
 
 __global__ void argmax_partials_kernel(const float *__restrict__ part_val, const int *__restrict__ part_idx, int M,
                                        int tiles_n, int *__restrict__ next) {
+    pdl_launch_dependents();
+    pdl_wait();
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= M) return;
     float best = -INFINITY;
@@ -921,7 +927,7 @@ __global__ void argmax_partials_kernel(const float *__restrict__ part_val, const
 }
 int argmax_partials(cudaStream_t st, const float *part_val, const int *part_idx, int M, int tiles_n, int *next_dev) {
     if (M <= 0) return WB_OK;
-    argmax_partials_kernel<<<cdiv(M, 8), 256, 0, st>>>(part_val, part_idx, M, tiles_n, next_dev);
+    WB_CUDA(launch_pdl(argmax_partials_kernel, dim3(cdiv(M, 8)), dim3(256), 0, st, part_val, part_idx, M, tiles_n, next_dev));
     WB_LAUNCHED();
     return WB_OK;
 }

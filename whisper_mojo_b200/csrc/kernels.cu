@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(256) ln_bf16_kernel(const float *__restrict__ 
                                                       const float *__restrict__ pos_emb,
                                                       const int *__restrict__ cur_tok, const int *__restrict__ pos_dev,
                                                       int vocab, int n_pos, float *__restrict__ x_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= rows) return;
     // D is a multiple of 128 for every supported config (heads * 64 with an even head count);
@@ -85,8 +87,8 @@ int ln_bf16(cudaStream_t st, const float *x, const float *gamma, const float *be
             __nv_bfloat16 *out_bf16, float *out_f32) {
     WB_ARG(D % 128 == 0 && D <= 1024, "ln_bf16: D=%d must be a multiple of 128 and <= 1024", D);
     if (rows <= 0) return WB_OK;
-    ln_bf16_kernel<false><<<cdiv(rows, 8), 256, 0, st>>>(x, gamma, beta, rows, D, out_bf16, out_f32, nullptr, nullptr,
-                                                          nullptr, nullptr, 0, 0, nullptr);
+    WB_CUDA(launch_pdl(ln_bf16_kernel<false>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, gamma, beta, rows, D, out_bf16,
+                       out_f32, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -96,8 +98,8 @@ int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const 
              __nv_bfloat16 *xn) {
     WB_ARG(D % 128 == 0 && D <= 1024, "embed_ln: D=%d must be a multiple of 128 and <= 1024", D);
     if (B <= 0) return WB_OK;
-    ln_bf16_kernel<true><<<cdiv(B, 8), 256, 0, st>>>(nullptr, gamma, beta, B, D, xn, nullptr, tok_emb, pos_emb,
-                                                      cur_tok, pos_dev, vocab, n_pos, x);
+    WB_CUDA(launch_pdl(ln_bf16_kernel<true>, dim3(cdiv(B, 8)), dim3(256), 0, st, nullptr, gamma, beta, B, D, xn, nullptr,
+                       tok_emb, pos_emb, cur_tok, pos_dev, vocab, n_pos, x));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -127,6 +129,8 @@ __device__ __forceinline__ uint4 ld_stream(const void *p) {
 
 __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p) {
     extern __shared__ float s_scores[];  // [H][smem_len]
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x, split = blockIdx.y;
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = lane & 7, sub = lane >> 3;
@@ -300,7 +304,7 @@ int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {
         smem_opted = smem;
     }
     dim3 grid(a.B, a.splits);
-    decode_attn_kernel<<<grid, a.H * 32, smem, st>>>(p);
+    WB_CUDA(launch_pdl(decode_attn_kernel, grid, dim3(a.H * 32), smem, st, p));
     WB_LAUNCHED();
     if (a.splits > 1) {
         decode_attn_combine_kernel<<<cdiv(a.B * a.H, 8), 256, 0, st>>>(a.ws, a.out, a.B, a.H, a.D, a.splits);
@@ -390,6 +394,8 @@ int greedy_init(cudaStream_t st, const GreedyState &g, int B, const int *prompt)
 // values all threads would read -- other threads use only per-row state, so there is no race.
 __global__ void greedy_advance_kernel(GreedyState g, int B, int mode, int next_prompt_token,
                                       const int *__restrict__ next) {
+    pdl_launch_dependents();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) {
         if (mode == 0) {
@@ -418,7 +424,7 @@ __global__ void greedy_advance_kernel(GreedyState g, int B, int mode, int next_p
     }
 }
 int greedy_advance(cudaStream_t st, const GreedyState &g, int B, int mode, int next_prompt_token, const int *next) {
-    greedy_advance_kernel<<<cdiv(B, 256), 256, 0, st>>>(g, B, mode, next_prompt_token, next);
+    WB_CUDA(launch_pdl(greedy_advance_kernel, dim3(cdiv(B, 256)), dim3(256), 0, st, g, B, mode, next_prompt_token, next));
     WB_LAUNCHED();
     return WB_OK;
 }

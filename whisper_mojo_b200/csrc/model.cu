@@ -14,6 +14,7 @@
 #include "model.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -90,6 +91,7 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
         set_error("wm_create: no CUDA device (this library has no CPU fallback)");
         return WB_ERR_CUDA;
     }
+    if (const char *e = getenv("WB_PDL")) g_pdl = atoi(e) != 0;  // A/B switch for programmatic dependent launch
     Model *m = new Model();
     m->cfg = *cfg;
     m->D = cfg->d_model, m->H = cfg->n_heads, m->L = cfg->n_layers, m->V = cfg->vocab_size;

@@ -236,13 +236,17 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: keep a private handle to it and point fd 1 at stderr for everything
+    # else (NCCL prints its version banner straight to fd 1 when the first communicator is created)
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = WhisperConfig.tiny()
@@ -410,7 +414,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "phases_ms_per_step": phases, "device_ms_each_step": step_ms, "decode_ms_each_step": step_decode_ms,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

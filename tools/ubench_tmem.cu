@@ -4,6 +4,7 @@
 //   (2) MUFU.EX2 throughput per SM.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ubench_tmem tools/ubench_tmem.cu
 #include <cstdio>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -64,6 +65,47 @@ __global__ void __launch_bounds__(512) mufu_kernel(int iters, long long *out, fl
     if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
 }
 
+// the exponential phase of the attention softmax in isolation: 128 scores per thread -> ex2(fma) -> row sum -> bf16x2
+// pack -> 16 x st.shared.v4; variant 1 drops the pack, variant 2 drops the sum, variant 3 only fma + ex2
+template <int VARIANT>
+__global__ void __launch_bounds__(256) exp_phase_kernel(int iters, const float *in, long long *out, float *sink) {
+    __shared__ uint4 sm[256 * 4];
+    float v[128];
+#pragma unroll
+    for (int t = 0; t < 128; t++) v[t] = in[(threadIdx.x * 128 + t) & 1023];
+    float l0 = 0.f, l1 = 0.f;
+    unsigned acc = 0;
+    const float c = 0.18033688f, nmc = -0.5f;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        uint32_t pk[64];
+#pragma unroll
+        for (int t = 0; t < 128; t += 2) {
+            const float p0 = ptx::ex2(fmaf(v[t], c, nmc));
+            const float p1 = ptx::ex2(fmaf(v[t + 1], c, nmc));
+            if (VARIANT != 2 && VARIANT != 3) l0 += p0, l1 += p1;
+            if (VARIANT == 0 || VARIANT == 2) {
+                __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+                pk[t >> 1] = *reinterpret_cast<uint32_t *>(&b);
+            } else {
+                pk[t >> 1] = __float_as_uint(p0) ^ __float_as_uint(p1);
+            }
+            v[t] = p0 - 1.0f, v[t + 1] = p1 - 1.0f;  // feed back so iterations depend on each other
+        }
+        if (VARIANT == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) sm[threadIdx.x * 4 + i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 64; i++) acc ^= pk[i];
+    }
+    long long t1 = clock64();
+    if (l0 + l1 == 12345.678f || acc == 0x12345u) sink[0] = l0 + l1 + sm[threadIdx.x].x;
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+}
+
+#include <cuda_bf16.h>
+
 int main() {
     long long *out;
     float *sink;
@@ -93,6 +135,24 @@ int main() {
         double clk = (double)h[0] / iters;
         printf("mufu.ex2 (+fadd): %d threads/SM: %.1f clk per 16 ex2/thread -> %.2f ex2/clk/SM\n", threads, clk,
                16.0 * threads / clk);
+    }
+    {
+        float *in;
+        cudaMalloc(&in, 1024 * 4);
+        cudaMemset(in, 0, 1024 * 4);
+        auto run = [&](auto kern, const char *name) {
+            for (int threads : {128, 256}) {
+                kern<<<148, threads>>>(200, in, out, sink);
+                cudaDeviceSynchronize();
+                cudaMemcpy(h, out, sizeof(long long), cudaMemcpyDeviceToHost);
+                printf("exp phase [%s], %d warps/SMSP: %.0f clk per 128 scores/thread (MUFU bound %d)\n", name, threads / 128,
+                       (double)h[0] / 200, 1024 * threads / 128);
+            }
+        };
+        run(exp_phase_kernel<0>, "fma+ex2+sum+pack+sts");
+        run(exp_phase_kernel<1>, "fma+ex2+sum");
+        run(exp_phase_kernel<2>, "fma+ex2+pack");
+        run(exp_phase_kernel<3>, "fma+ex2");
     }
     return 0;
 }

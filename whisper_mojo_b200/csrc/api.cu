@@ -456,6 +456,8 @@ static int staged(Model *m, const Tin *in_host, size_t n_in, Tout *out_host, siz
     return rc;
 }
 
+namespace wb { extern unsigned long long *g_ea_dbg; extern int g_ea_dbg_cta1; }
+
 extern "C" {
 
 int wm_logmel_dev(wm_model h, const float *pcm_dev, int n_chunks, float *mel_dev) {
@@ -750,6 +752,42 @@ int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, in
     if (rc == WB_OK) ok(cudaMemcpy(f32, qkv_host, nin * 4, cudaMemcpyHostToDevice));
     if (rc == WB_OK) rc = convert_f32_bf16(0, f32, qkv, nin);
     if (rc == WB_OK) rc = impl ? encoder_attention_tc(0, qkv, o, B, S, H, D) : encoder_attention_ref(0, qkv, o, B, S, H, D);
+    if (rc == WB_OK && impl && getenv("WB_EA_DBG")) {  // timestamp dump of two CTAs (development aid)
+        unsigned long long *d = nullptr;
+        const size_t nd = 2 * 2 * 16 * 8 + 2 + 512;
+        ok(cudaMalloc((void **)&d, nd * 8));
+        ok(cudaMemset(d, 0, nd * 8));
+        g_ea_dbg = d, g_ea_dbg_cta1 = atoi(getenv("WB_EA_DBG"));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        cudaEventRecord(e0, 0);
+        rc = encoder_attention_tc(0, qkv, o, B, S, H, D);
+        cudaEventRecord(e1, 0);
+        g_ea_dbg = nullptr;
+        ok(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        std::vector<unsigned long long> hd(nd);
+        ok(cudaMemcpy(hd.data(), d, nd * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = hd[(0 * 2 + 1) * 16 * 8];  // CTA 0, MMA, block 0, event 0
+        const size_t tail = 2 * 2 * 16 * 8;
+        fprintf(stderr, "EA kernel %.3f ms (B=%d); traced CTAs 0 (sm %llu) and %d (sm %llu); CTAs on CTA 0's SM:", ms, B, hd[tail],
+                g_ea_dbg_cta1, hd[tail + 1]);
+        for (int i = 1; i < 512; i++)
+            if (hd[tail + 2 + i] == hd[tail + 2]) fprintf(stderr, " %d", i);
+        fprintf(stderr, "\n");
+        for (int c = 0; c < 2; c++) {
+            fprintf(stderr, "CTA slot %d: blk | mma: S_issue p_full v_full | smx: s_full ld_done shift_done exp_done pv_waited fence_done arrived (SM clocks)\n", c);
+            for (int g = 0; g < 12; g++) {
+                fprintf(stderr, "%3d |", g);
+                for (int e = 0; e < 3; e++) fprintf(stderr, " %8.0f", ((double)hd[((c * 2 + 1) * 16 + g) * 8 + e] - (double)t0));
+                fprintf(stderr, " |");
+                for (int e = 0; e < 7; e++) fprintf(stderr, " %8.0f", ((double)hd[((c * 2 + 0) * 16 + g) * 8 + e] - (double)t0));
+                fprintf(stderr, "\n");
+            }
+        }
+        cudaFree(d);
+    }
     if (rc == WB_OK) {
         bf16_to_f32_kernel<<<(unsigned)((nout + 255) / 256), 256>>>(o, f32, nout);
         ok(cudaGetLastError());

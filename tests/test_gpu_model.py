@@ -207,6 +207,29 @@ def test_kv_cache_cross_attention_form_still_matches_oracle(setup):
     assert np.abs(la - lb).max() <= LOGIT_MAX
 
 
+def test_split_k_decode_path_matches_oracle(setup):
+    """decode_split_k = 2 forces the large-batch decode form at test sizes: the residual GEMMs run split-K into
+    fp32 partials and the following LayerNorm kernel sums them into x in a fixed order.  It must meet the same
+    oracle bounds as the fused-epilogue form, agree with it on clear steps, and stay batch invariant."""
+    cfg, mel, m, om, enc_ref = setup
+    ms, _ = build(cfg, decode_split_k=2)
+    m0, _ = build(cfg, decode_split_k=0)
+    ts, lsn = ms.transcribe_batch(mel)
+    for i in range(len(mel)):
+        ref, mg = om.greedy(enc_ref[i], margins=True)
+        ok, msg = tokens_agree_up_to_margin(ts[i, :lsn[i]], ref, mg, MARGIN_TAU)
+        assert ok, f"chunk {i}: {msg}"
+    t1, l1 = ms.transcribe_batch(mel[1:2])
+    assert np.array_equal(t1[0], ts[1])
+    forced = np.stack([np.concatenate([np.array(cfg.prompt), np.random.default_rng(30 + i).integers(0, cfg.vocab_size, 8)])
+                       for i in range(len(mel))]).astype(np.int32)
+    enc = torch.from_numpy(enc_ref).cuda()
+    la, lb = ms.teacher_forced(enc, forced), m0.teacher_forced(enc, forced)
+    ref = np.stack([om.teacher_forced(enc_ref[i], forced[i]) for i in range(len(mel))])
+    assert np.abs(la - ref).max() <= LOGIT_MAX and np.abs(lb - ref).max() <= LOGIT_MAX
+    assert np.abs(la - lb).max() <= LOGIT_MAX / 2
+
+
 def test_two_decode_lanes_equal_one_lane():
     """>= 256 chunks run as two half-batches on two streams inside one CUDA graph; ids must not change."""
     cfg = WhisperConfig.micro()

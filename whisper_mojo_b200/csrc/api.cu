@@ -384,6 +384,14 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     if (!strcmp(key, "gemm_impl")) m->gemm_impl = (int)value;
     else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
     else if (!strcmp(key, "frontend_impl")) m->frontend_impl = (int)value;
+    else if (!strcmp(key, "decode_split_k")) {
+        WB_ARG(value >= 0 && value <= 2, "decode_split_k: 0 = off, 1 = for batches >= 512 (default), 2 = always");
+        m->decode_split_k = (int)value;
+        if (m->tr_cache) {  // the captured decode graph holds the old kernel sequence
+            cache_destroy(m->tr_cache);
+            m->tr_cache = nullptr;
+        }
+    }
     else if (!strcmp(key, "pdl")) {  // process-wide; captured decode graphs keep the setting they were built with
         g_pdl = value != 0;
         if (m->tr_cache) {

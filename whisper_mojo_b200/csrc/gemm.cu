@@ -33,6 +33,7 @@ struct GemmDev {
     int rows_per_batch, batches, N, K;
     int tiles_m_per_batch, tiles_n, num_kb, kb_per_tap, taps;
     int a_row_off[3];
+    int split_koff;  // > 0: split-K, "batch" b covers K columns [b * split_koff, (b + 1) * split_koff) of A and W
     const float *bias;
     int epi;
     void *out[3];
@@ -525,8 +526,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                     const uint32_t bar = ptx::mapa_u32(&full_bar[stage], 0);
                     uint8_t *sa = tiles + stage * PAIR_STAGE_BYTES, *sb = sa + A_STAGE_BYTES;
                     const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * BK;
-                    ptx::tma_load_3d_pair(sa, &P.a_map[tap], bar, c0, m0 + p.a_row_off[tap], b);
-                    ptx::tma_load_2d_pair(sb, &P.b_map, bar, kb * BK, n0);
+                    const int koff = b * p.split_koff;  // split-K: the "batch" index selects a K slice, not rows
+                    ptx::tma_load_3d_pair(sa, &P.a_map[tap], bar, c0 + koff, m0 + p.a_row_off[tap], p.split_koff ? 0 : b);
+                    ptx::tma_load_2d_pair(sb, &P.b_map, bar, kb * BK + koff, n0);
                     if (++stage == PAIR_STAGES) stage = 0, phase ^= 1;
                 }
             }
@@ -611,7 +613,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                         o[4 * j] = __uint_as_float(v[c & 1][4 * j]) + bv.x, o[4 * j + 1] = __uint_as_float(v[c & 1][4 * j + 1]) + bv.y;
                         o[4 * j + 2] = __uint_as_float(v[c & 1][4 * j + 2]) + bv.z, o[4 * j + 3] = __uint_as_float(v[c & 1][4 * j + 3]) + bv.w;
                     }
-                    if (EPI == EPI_RESID_F32) {
+                    if (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
 #pragma unroll
                         for (int j = 0; j < 8; j++)
                             *reinterpret_cast<float4 *>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
@@ -799,6 +801,16 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
     p.taps = d.taps;
     p.kb_per_tap = d.Cin / BK;
     p.num_kb = d.taps * p.kb_per_tap;
+    p.split_koff = 0;
+    if (d.split_k > 1) {
+        WB_ARG(d.taps == 1 && d.batches == 1 && d.epi == EPI_STORE_F32 && !d.bias && d.n_seg_ptrs == 1 && !d.dyn_off &&
+                   impl != GEMM_IMPL_REF && d.Cin % (d.split_k * BK) == 0,
+               "gemm: split_k needs a plain bias-free EPI_STORE_F32 GEMM with K %% (64 * split_k) == 0 on the tcgen05 path");
+        p.split_koff = d.Cin / d.split_k;
+        p.batches = d.split_k;  // K slices ride on the batch index of the tile scheduler and of the output rows
+        p.num_kb = p.split_koff / BK;
+        p.kb_per_tap = p.num_kb;
+    }
     p.bias = d.bias;
     p.epi = d.epi;
     for (int i = 0; i < 3; i++) p.out[i] = d.out[i], p.out_ld[i] = d.out_ld[i], p.dyn_mult[i] = d.dyn_mult[i];
@@ -863,8 +875,8 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
     // CTA-pair kernel: always for a full wave of pair tiles; for the decode-step GEMMs (M = batch <= 2048) already
     // from 12 pair tiles on (measured: 10-15 % faster than 48..288 single-CTA tiles) unless the output goes through
     // the device-side KV-cache offset (per-thread stores, where the single-CTA kernel wins).
-    const int64_t pair_tiles = (int64_t)d.batches * pair_tiles_m * cdiv(d.N, 256);
-    const bool want_pair = impl == GEMM_IMPL_TC_PAIR ||
+    const int64_t pair_tiles = (int64_t)p.batches * pair_tiles_m * cdiv(d.N, 256);
+    const bool want_pair = impl == GEMM_IMPL_TC_PAIR || d.split_k > 1 ||
                            (impl == GEMM_IMPL_TC && (pair_tiles >= sms / 2 || (pair_tiles >= 12 && !d.dyn_off)));
     if (pair_ok && want_pair) {
         GemmPairParams Q;
@@ -875,33 +887,35 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
         Q.d = p;
         Q.pair_tiles_m_per_batch = pair_tiles_m;
         Q.pair_tiles_n = cdiv(d.N, bn2);
-        const int total = d.batches * pair_tiles_m * Q.pair_tiles_n;
+        const int total = p.batches * pair_tiles_m * Q.pair_tiles_n;
         const int grid = 2 * std::min(total, sms / 2);
         switch (d.epi) {
             case EPI_STORE_BF16:
             case EPI_GELU_BF16:
-            case EPI_RESID_F32: {
-                // plain [rows][N] output -> coalesced TMA stores (bf16) / residual add by TMA reduce (fp32: the SM
-                // never reads the old values)
-                const int esz = d.epi == EPI_RESID_F32 ? 4 : 2;
+            case EPI_RESID_F32:
+            case EPI_STORE_F32: {
+                // plain [rows][N] output -> coalesced TMA stores / residual add by TMA reduce (fp32: the SM never
+                // reads the old values)
+                const int esz = (d.epi == EPI_RESID_F32 || d.epi == EPI_STORE_F32) ? 4 : 2;
                 const bool plain = d.n_seg_ptrs == 1 && !d.dyn_off && p.seg_cols == d.N && (d.out_ld[0] * esz) % 16 == 0 &&
                                    (reinterpret_cast<uintptr_t>(d.out[0]) & 15) == 0 && g_tma_out;
                 if (plain) {
-                    const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.rows_per_batch, (uint64_t)d.batches};
+                    const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.rows_per_batch, (uint64_t)p.batches};
                     const uint64_t str[2] = {(uint64_t)d.out_ld[0] * esz, (uint64_t)d.rows_per_batch * d.out_ld[0] * esz};
                     const uint32_t box[3] = {32, 32, 1};
                     WB_CHECK(make_tmap_any(&Q.out_map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                                            esz == 4 ? 128 : 64, d.out[0], 3, dims, str, box));
                     if (d.epi == EPI_STORE_BF16) return launch_pair_bn<EPI_STORE_BF16, true>(st, Q, grid, bn2);
                     if (d.epi == EPI_GELU_BF16) return launch_pair_bn<EPI_GELU_BF16, true>(st, Q, grid, bn2);
+                    if (d.epi == EPI_STORE_F32) return launch_pair_bn<EPI_STORE_F32, true>(st, Q, grid, bn2);
                     return launch_pair_bn<EPI_RESID_F32, true>(st, Q, grid, bn2);
                 }
                 if (d.epi == EPI_STORE_BF16) return launch_pair_bn<EPI_STORE_BF16>(st, Q, grid, bn2);
                 if (d.epi == EPI_GELU_BF16) return launch_pair_bn<EPI_GELU_BF16>(st, Q, grid, bn2);
+                if (d.epi == EPI_STORE_F32) return launch_pair_bn<EPI_STORE_F32>(st, Q, grid, bn2);
                 return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
             }
             case EPI_ARGMAX: return launch_pair<EPI_ARGMAX, 256, false>(st, Q, grid);
-            case EPI_STORE_F32: return launch_pair_bn<EPI_STORE_F32>(st, Q, grid, bn2);
             case EPI_GELU_POS_F32: return launch_pair_bn<EPI_GELU_POS_F32>(st, Q, grid, bn2);
         }
     }

@@ -52,6 +52,12 @@ struct GemmDesc {
     float *part_val = nullptr;   // EPI_ARGMAX: [M][gemm_tiles_n(N)]
     int *part_idx = nullptr;
     float *logits = nullptr;  // EPI_ARGMAX: optional full logits [M][N]
+    // Split-K (CTA-pair kernel, plain GEMM, EPI_STORE_F32 without bias): the K = taps * Cin reduction is cut into
+    // split_k slices of equal length (a multiple of 64); slice s writes its fp32 partial product to rows
+    // [s * rows_per_batch, (s + 1) * rows_per_batch) of the output.  The slices run as extra tiles, so a small-M GEMM
+    // with a long K (decode: M = 2048, K = 2304) spreads over the whole chip; the caller sums the slices in a
+    // fixed order (resid_ln).
+    int split_k = 1;
 };
 
 // Number of argmax partial slots per row: two per 128-column tile (one per epilogue column half).

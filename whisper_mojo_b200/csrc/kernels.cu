@@ -15,7 +15,10 @@ namespace wb {
 // ---------------------------------------------------------------------------------------------
 // LayerNorm fp32 -> bf16: one warp per row.
 // ---------------------------------------------------------------------------------------------
-template <bool EMBED>
+enum { LN_PLAIN = 0, LN_EMBED = 1, LN_RESID = 2 };
+// MODE LN_RESID: x[row] += bias + sum_s part[s][row] (fixed order: deterministic) before the LayerNorm -- the second
+// half of a split-K residual GEMM fused with the LayerNorm that follows it; gamma == nullptr skips the LN output.
+template <int EMBED>
 __global__ void __launch_bounds__(256) ln_bf16_kernel(const float *__restrict__ x_in, const float *__restrict__ gamma,
                                                       const float *__restrict__ beta, int rows, int D,
                                                       __nv_bfloat16 *__restrict__ out_bf16,
@@ -24,7 +27,10 @@ __global__ void __launch_bounds__(256) ln_bf16_kernel(const float *__restrict__ 
                                                       const float *__restrict__ tok_emb,
                                                       const float *__restrict__ pos_emb,
                                                       const int *__restrict__ cur_tok, const int *__restrict__ pos_dev,
-                                                      int vocab, int n_pos, float *__restrict__ x_out) {
+                                                      int vocab, int n_pos, float *__restrict__ x_out,
+                                                      // LN_RESID only:
+                                                      const float *__restrict__ part, int n_split,
+                                                      long long split_stride, const float *__restrict__ bias) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -34,7 +40,25 @@ __global__ void __launch_bounds__(256) ln_bf16_kernel(const float *__restrict__ 
     float4 v[8];
     const int nvec = D >> 7;
     float s = 0.f, q = 0.f;
-    if (EMBED) {
+    if (EMBED == LN_RESID) {
+        float4 *xr = reinterpret_cast<float4 *>(x_out + (size_t)row * D);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < nvec) {
+                float4 a = xr[i * 32 + lane];
+                if (bias) {
+                    const float4 b = reinterpret_cast<const float4 *>(bias)[i * 32 + lane];
+                    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+                }
+                for (int sidx = 0; sidx < n_split; sidx++) {
+                    const float4 pp = reinterpret_cast<const float4 *>(part + (size_t)sidx * split_stride + (size_t)row * D)[i * 32 + lane];
+                    a.x += pp.x, a.y += pp.y, a.z += pp.z, a.w += pp.w;
+                }
+                v[i] = a;
+                xr[i * 32 + lane] = a;
+            }
+        if (!gamma) return;
+    } else if (EMBED == LN_EMBED) {
         int tok = cur_tok[row];
         tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
         int pos = *pos_dev;
@@ -87,8 +111,19 @@ int ln_bf16(cudaStream_t st, const float *x, const float *gamma, const float *be
             __nv_bfloat16 *out_bf16, float *out_f32) {
     WB_ARG(D % 128 == 0 && D <= 1024, "ln_bf16: D=%d must be a multiple of 128 and <= 1024", D);
     if (rows <= 0) return WB_OK;
-    WB_CUDA(launch_pdl(ln_bf16_kernel<false>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, gamma, beta, rows, D, out_bf16,
-                       out_f32, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr));
+    WB_CUDA(launch_pdl(ln_bf16_kernel<LN_PLAIN>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, gamma, beta, rows, D, out_bf16,
+                       out_f32, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, 0, nullptr));
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+int resid_ln(cudaStream_t st, float *x, const float *part, int n_split, const float *bias, const float *gamma,
+             const float *beta, int rows, int D, __nv_bfloat16 *out_bf16) {
+    WB_ARG(D % 128 == 0 && D <= 1024, "resid_ln: D=%d must be a multiple of 128 and <= 1024", D);
+    WB_ARG(x && part && n_split >= 1 && (!gamma || (beta && out_bf16)), "resid_ln: bad arguments");
+    if (rows <= 0) return WB_OK;
+    WB_CUDA(launch_pdl(ln_bf16_kernel<LN_RESID>, dim3(cdiv(rows, 8)), dim3(256), 0, st, nullptr, gamma, beta, rows, D, out_bf16,
+                       nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, x, part, n_split, (long long)rows * D, bias));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -98,8 +133,8 @@ int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const 
              __nv_bfloat16 *xn) {
     WB_ARG(D % 128 == 0 && D <= 1024, "embed_ln: D=%d must be a multiple of 128 and <= 1024", D);
     if (B <= 0) return WB_OK;
-    WB_CUDA(launch_pdl(ln_bf16_kernel<true>, dim3(cdiv(B, 8)), dim3(256), 0, st, nullptr, gamma, beta, B, D, xn, nullptr,
-                       tok_emb, pos_emb, cur_tok, pos_dev, vocab, n_pos, x));
+    WB_CUDA(launch_pdl(ln_bf16_kernel<LN_EMBED>, dim3(cdiv(B, 8)), dim3(256), 0, st, nullptr, gamma, beta, B, D, xn, nullptr,
+                       tok_emb, pos_emb, cur_tok, pos_dev, vocab, n_pos, x, nullptr, 0, 0, nullptr));
     WB_LAUNCHED();
     return WB_OK;
 }

@@ -10,6 +10,12 @@ namespace wb {
 int ln_bf16(cudaStream_t st, const float *x, const float *gamma, const float *beta, int rows, int D,
             __nv_bfloat16 *out_bf16, float *out_f32);
 
+// Second half of a split-K residual GEMM fused with the LayerNorm that follows it (layers.mojo:456-461,486-491,
+// 515-517 + the next block's LayerNorm): x[row] += bias + part[0][row] + ... + part[n_split-1][row] in that
+// fixed order, then out_bf16[row] = LN(x[row]) unless gamma is null.  part is [n_split][rows][D] fp32.
+int resid_ln(cudaStream_t st, float *x, const float *part, int n_split, const float *bias, const float *gamma,
+             const float *beta, int rows, int D, __nv_bfloat16 *out_bf16);
+
 // Decoder input (whisper.mojo:138-149) fused with the first LayerNorm of layer 0:
 //   x[b] = token_emb[cur_tok[b]] + pos_emb[*pos];  xn[b] = LN(x[b]) in bf16.
 int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const int *cur_tok, const int *pos_dev,

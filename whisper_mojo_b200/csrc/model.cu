@@ -386,6 +386,7 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
         A(&ln.part_idx, (size_t)ln.B * slots);
         A(&ln.next, ln.B);
         A(&ln.attn_ws, (size_t)ln.B * ln.cross_splits * m->H * 66);
+        A(&ln.part, (size_t)4 * ln.B * D);  // split-K partial products of the residual GEMMs
         if (c->cross_impl == 1) {
             A(&ln.qp, (size_t)ln.B * m->H * D);
             A(&ln.ctx, (size_t)ln.B * m->H * D);
@@ -487,12 +488,38 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         return embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, ln.g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
                         m->dec[0].ln1_b, ln.x, ln.xn);
     }));
+    // x += A W^T + bias followed by xn = LN(x; g, b)  (g == nullptr: no LayerNorm follows).
+    //  * plain: residual-add GEMM epilogue, then the LayerNorm kernel;
+    //  * split-K (tcgen05 path, batch large enough): the GEMM with M = batch and N = D only fills 32 CTAs and its K
+    //    loop is what takes the time, so K is cut into slices that run as extra tiles (fp32 partials), and the
+    //    LayerNorm kernel sums them into x in a fixed order first -- same number of launches, whole chip busy.
+    auto resid_gemm_ln = [&](int cat, const bf16 *A, int K, const bf16 *Wt, const float *bias, const float *g,
+                             const float *bb) -> int {
+        int split = 1;
+        if (impl == GEMM_IMPL_TC && ln.part && (m->decode_split_k == 2 || (m->decode_split_k == 1 && B >= 512)))
+            for (int sp : {4, 3, 2})
+                if (K % (64 * sp) == 0 && K / sp >= 192) {
+                    split = sp;
+                    break;
+                }
+        if (split > 1) {
+            GemmDesc gd = plain_gemm(A, B, K, Wt, D, nullptr, EPI_STORE_F32, ln.part, D);
+            gd.split_k = split;
+            WB_CHECK(timed_kernel(m, st, cat, [&] { return gemm_run(st, gd, impl); }));
+            return timed_kernel(m, st, TK_LN, [&] { return resid_ln(st, ln.x, ln.part, split, bias, g, bb, B, D, ln.xn); });
+        }
+        WB_CHECK(timed_kernel(m, st, cat, [&] {
+            return gemm_run(st, plain_gemm(A, B, K, Wt, D, bias, EPI_RESID_F32, ln.x, D), impl);
+        }));
+        if (!g) return WB_OK;
+        return timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, g, bb, B, D, ln.xn, nullptr); });
+    };
     for (int l = 0; l < m->L; l++) {
         const LayerDev &d = m->dec[l];
         bf16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
         bf16 *ck = c->cross_kv ? c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off : nullptr;
         bf16 *cv = ck ? ck + cross_seg : nullptr;
-        if (l > 0) WB_CHECK(timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, d.ln1_g, d.ln1_b, B, D, ln.xn, nullptr); }));
+        // (xn = LN1(x) was produced by embed_ln / by the previous layer's fc2 step)
         {  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
             GemmDesc g = plain_gemm(ln.xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, ln.q, D);
             g.n_seg_ptrs = 3, g.seg_cols = D;
@@ -506,11 +533,8 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
         a.splits = 1, a.ws = nullptr;
         WB_CHECK(timed_kernel(m, st, TK_SELF, [&] { return decode_attention(st, a); }));
-        WB_CHECK(timed_kernel(m, st, TK_O, [&] {
-            return gemm_run(st, plain_gemm(ln.attn, B, D, d.wo, D, d.bo, EPI_RESID_F32, ln.x, D), impl);
-        }));
+        WB_CHECK(resid_gemm_ln(TK_O, ln.attn, D, d.wo, d.bo, d.ln2_g, d.ln2_b));
         // cross attention over the encoder positions (layers.mojo:463-488)
-        WB_CHECK(timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, d.ln2_g, d.ln2_b, B, D, ln.xn, nullptr); }));
         if (c->cross_impl == 1) {
             // absorbed form: q' = (Wk_h^T Wq_h) x + ..., attend over enc_out, out = (Wo Wv_h) ctx_h + ...
             const int HD = m->H * D;
@@ -519,9 +543,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
             }));
             const bf16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
             WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
-            WB_CHECK(timed_kernel(m, st, TK_CO, [&] {
-                return gemm_run(st, plain_gemm(ln.ctx, B, HD, d.wov, D, d.bov, EPI_RESID_F32, ln.x, D), impl);
-            }));
+            WB_CHECK(resid_gemm_ln(TK_CO, ln.ctx, HD, d.wov, d.bov, d.ln3_g, d.ln3_b));
         } else {
             WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
                 return gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, ln.q, D), impl);
@@ -530,23 +552,19 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
             a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
             a.splits = ln.cross_splits, a.ws = ln.attn_ws;
             WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return decode_attention(st, a); }));
-            WB_CHECK(timed_kernel(m, st, TK_CO, [&] {
-                return gemm_run(st, plain_gemm(ln.attn, B, D, d.cwo, D, d.cbo, EPI_RESID_F32, ln.x, D), impl);
-            }));
+            WB_CHECK(resid_gemm_ln(TK_CO, ln.attn, D, d.cwo, d.cbo, d.ln3_g, d.ln3_b));
         }
-        // MLP (layers.mojo:490-517)
-        WB_CHECK(timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, d.ln3_g, d.ln3_b, B, D, ln.xn, nullptr); }));
+        // MLP (layers.mojo:490-517); the LayerNorm after fc2 is the next layer's attn_ln, or the decoder's ln_post
+        // in front of the logits (whisper.mojo:156-158), or none on a prefill step
         WB_CHECK(timed_kernel(m, st, TK_FC1, [&] {
             return gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, ln.h, m->F), impl);
         }));
-        WB_CHECK(timed_kernel(m, st, TK_FC2, [&] {
-            return gemm_run(st, plain_gemm(ln.h, B, m->F, d.w2, D, d.b2, EPI_RESID_F32, ln.x, D), impl);
-        }));
+        const bool last = l + 1 == m->L;
+        const float *ng = last ? (with_logits ? W + m->lay.dec_ln_w : nullptr) : m->dec[l + 1].ln1_g;
+        const float *nb = last ? (with_logits ? W + m->lay.dec_ln_b : nullptr) : m->dec[l + 1].ln1_b;
+        WB_CHECK(resid_gemm_ln(TK_FC2, ln.h, m->F, d.w2, d.b2, ng, nb));
     }
     if (with_logits) {  // whisper.mojo:156-166 + argmax :198,219
-        WB_CHECK(timed_kernel(m, st, TK_LN, [&] {
-            return ln_bf16(st, ln.x, W + m->lay.dec_ln_w, W + m->lay.dec_ln_b, B, D, ln.xn, nullptr);
-        }));
         GemmDesc g = plain_gemm(ln.xn, B, D, m->tok_emb_bf16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
         g.part_val = ln.part_val, g.part_idx = ln.part_idx;
         g.logits = (store_logits || impl == GEMM_IMPL_REF) ? ln.logits : nullptr;

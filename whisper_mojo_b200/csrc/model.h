@@ -61,6 +61,7 @@ struct Model {
     bool own_stream = false;
     int gemm_impl = 1, attn_impl = 1, frontend_impl = 1,  // frontend: 0 = fp32 FMA DFT, 1 = TF32x3 tensor-core DFT
          use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048,
+        decode_split_k = 1,  // split-K residual GEMMs + fused residual/LayerNorm in the decode step
         decode_lanes = 1,  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
         cross_impl = 1;    // 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (D <= 384)
     Layout lay;
@@ -94,7 +95,7 @@ struct Model {
 // other lane's HBM-bound cross-attention.
 struct Lane {
     int B = 0, b_off = 0;
-    float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr;
+    float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr, *part = nullptr;
     bf16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *qp = nullptr, *ctx = nullptr;
     int *part_idx = nullptr, *next = nullptr;
     int cross_splits = 1;

@@ -20,14 +20,18 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--graph", type=int, default=0)
 ap.add_argument("--lanes", type=int, default=2)
 ap.add_argument("--enc-batch", type=int, default=0)
+ap.add_argument("--config", default="tiny", choices=["tiny", "small"])
+ap.add_argument("--cross-impl", type=int, default=-1)
 a = ap.parse_args()
-base = WhisperConfig.tiny()
+base = WhisperConfig.tiny() if a.config == "tiny" else WhisperConfig.small_shaped()
 cfg = WhisperConfig(**{**base.__dict__, "max_iters": a.iters})
 m = Whisper(cfg, stream=torch.cuda.current_stream().cuda_stream)
 m.set_option("use_graph", a.graph)
 m.set_option("decode_lanes", a.lanes)
 if a.enc_batch:
     m.set_option("enc_batch", a.enc_batch)
+if a.cross_impl >= 0:
+    m.set_option("cross_impl", a.cross_impl)
 m.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
 pcm = synth_pcm_gpu(a.chunks, cfg.n_samples, torch.device("cuda"), 1234)
 for r in range(a.reps):

@@ -104,9 +104,77 @@ __global__ void __launch_bounds__(256) exp_phase_kernel(int iters, const float *
     if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
 }
 
+// Where do the rows of an M = 64 accumulator live in TMEM?  D[i][n] = i + 1 for a 64 x 16 product; every lane dumps
+// column 0.  (Both operands K-major, no swizzle would need other descriptors: the 128B-swizzle atoms of the kernels
+// are reused -- A is [64 rows][64 k] with only k = 0 set, B is [16 rows][64 k] with k = 0 = 1.)
+__global__ void __launch_bounds__(128) m64_layout_kernel(float *out) {
+    __shared__ __align__(1024) uint8_t sA[64 * 128];
+    __shared__ __align__(1024) uint8_t sB[16 * 128];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t holder;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 64 * 128 / 2; i += 128) reinterpret_cast<__nv_bfloat16 *>(sA)[i] = __float2bfloat16(0.f);
+    for (int i = threadIdx.x; i < 16 * 128 / 2; i += 128) reinterpret_cast<__nv_bfloat16 *>(sB)[i] = __float2bfloat16(0.f);
+    __syncthreads();
+    // element (row r, k = 0): 16-byte chunk 0 of row r sits at chunk (0 ^ (r & 7)) under the 128B swizzle
+    if (threadIdx.x < 64) reinterpret_cast<__nv_bfloat16 *>(sA + threadIdx.x * 128 + ((0 ^ (threadIdx.x & 7)) << 4))[0] = __float2bfloat16((float)(threadIdx.x + 1));
+    if (threadIdx.x < 16) reinterpret_cast<__nv_bfloat16 *>(sB + threadIdx.x * 128 + ((0 ^ (threadIdx.x & 7)) << 4))[0] = __float2bfloat16(1.f);
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc(&holder, 32);
+        ptx::tmem_relinquish();
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t base = holder;
+    // zero the 32 columns first so untouched lanes read 0
+    {
+        uint32_t z[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) z[i] = 0;
+        ptx::tmem_st_32x32b_x32(base + ((uint32_t)(warp * 32) << 16), z);
+        ptx::tmem_st_wait();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = ptx::umma_idesc_bf16(64, 16, 0, 0);
+        ptx::mma_bf16_ss(base, ptx::umma_desc_sw128(ptx::smem_u32(sA), 1, 64), ptx::umma_desc_sw128(ptx::smem_u32(sB), 1, 64),
+                         idesc, 0);
+        ptx::mma_commit(&bar);
+    }
+    ptx::mbar_wait(&bar, 0);
+    ptx::tc_fence_after();
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(base + ((uint32_t)(warp * 32) << 16), v);
+    ptx::tmem_ld_wait();
+    out[threadIdx.x * 2] = __uint_as_float(v[0]);
+    out[threadIdx.x * 2 + 1] = __uint_as_float(v[15]);
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(base, 32);
+}
+
 #include <cuda_bf16.h>
 
 int main() {
+    {
+        float *o, ho[256];
+        cudaMalloc(&o, 256 * 4);
+        cudaMemset(o, 0, 256 * 4);
+        m64_layout_kernel<<<1, 128>>>(o);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(ho, o, 256 * 4, cudaMemcpyDeviceToHost);
+        printf("M=64 accumulator layout (%s): lane -> row+1 (col 0 | col 15)\n", cudaGetErrorString(e));
+        for (int l = 0; l < 128; l++) printf("%s%3.0f|%3.0f", (l % 16 == 0) ? "\n  " : " ", ho[2 * l], ho[2 * l + 1]);
+        printf("\n");
+    }
     long long *out;
     float *sink;
     cudaMalloc(&out, 4096 * sizeof(long long));

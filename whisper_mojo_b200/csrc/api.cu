@@ -403,7 +403,7 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
     else if (!strcmp(key, "cross_impl")) {
         WB_ARG(value == 0 || (value == 1 && cross_attn_absorbed_supported(m->D, m->H)),
-               "cross_impl must be 0, or 1 with d_model <= 384");
+               "cross_impl must be 0, or 1 with d_model <= 768 and <= 16 heads");
         m->cross_impl = (int)value;
     } else if (!strcmp(key, "decode_lanes")) {
         WB_ARG(value == 1 || value == 2, "decode_lanes must be 1 or 2");

@@ -30,12 +30,14 @@ int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
                    uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
 
 static constexpr int XA_THREADS = 224;
-static constexpr int ATOM_BYTES = 128 * 64 * 2;  // [128 keys x 64 channels] bf16
 static constexpr int QATOM_BYTES = 16 * 64 * 2;  // [16 heads x 64 channels]
-static constexpr int XA_MAX_ATOMS = 6;           // D <= 384
+// Keys per block: 128 for D <= 384 (96 KB stages); 64 for D up to 768 -- the stage stays 96 KB, the score UMMAs run
+// with M = 64 (accumulator row i in TMEM lane 32 (i / 16) + i % 16, measured with tools/ubench_tmem.cu), so only the
+// first 16 lanes of every softmax warp own a key.
+static constexpr int xa_keys(int atoms) { return atoms <= 6 ? 128 : 64; }
 
 struct CrossAttnParams {
-    CUtensorMap enc_map;  // dims (D, S, B), box (64, 128, 1)
+    CUtensorMap enc_map;  // dims (D, S, B), box (64, KEYS, 1)
     CUtensorMap q_map;    // dims (D, H, B), box (64, 16, 1): rows >= H are zero filled
     __nv_bfloat16 *ctx;   // [B][H*D]
     int B, S, D, H, n_blocks, atoms;
@@ -70,14 +72,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 template <int ATOMS>
 __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(const __grid_constant__ CrossAttnParams P) {
+    constexpr int KEYS = xa_keys(ATOMS);
+    constexpr int ATOM_BYTES = KEYS * 64 * 2;  // [KEYS x 64 channels] bf16
+    constexpr int XA_MAX_ATOMS = ATOMS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int atoms = ATOMS;
     constexpr int stage_bytes = atoms * ATOM_BYTES;
-    uint8_t *sEnc = base;                                  // [2][atoms][128 x 64]
+    uint8_t *sEnc = base;                                  // [2][atoms][KEYS x 64]
     uint8_t *sQ = base + 2 * stage_bytes;                  // [atoms][16 x 64]
-    uint8_t *sP = sQ + XA_MAX_ATOMS * QATOM_BYTES;         // [2][16 x 64]   P^T, keys 0-63 | 64-127
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * QATOM_BYTES);
+    uint8_t *sP = sQ + XA_MAX_ATOMS * QATOM_BYTES;         // [KEYS / 64][16 x 64]   P^T, keys 0-63 | 64-127
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + (KEYS / 64) * QATOM_BYTES);
     // enc_full[stage][atom]: one barrier per 64-channel atom, so the score MMAs of an atom issue as soon as it has
     // landed instead of after the whole 96 KB stage (the S MMAs are issue bound: ~1 us per block otherwise sits
     // between "stage arrived" and "scores ready", and with only two stages that latency caps the HBM stream)
@@ -120,11 +125,13 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    // TMEM columns: score partials S[stage][part] @ 16 * (stage * n_acc + part) (< 96), context C_m of chunk parity
-    // p @ 128 + 128 p + 32 m (two context buffers: the epilogue of chunk i runs under the first block of chunk i+1).
+    // TMEM columns: score partials S[stage][part] @ 16 * (stage * n_acc + part), then the context accumulators C_m of
+    // chunk parity p @ 32 n_acc + 16 (p n_acc + m) (two context buffers: the epilogue of chunk i runs under the first
+    // block of chunk i+1); 64 n_acc columns in all (192 for D = 384, 384 for D = 768).
     // Back-to-back MMAs into one accumulator serialise (~45 ns each), so the K = D reduction of the scores is
     // split into one partial accumulator per atom pair and the issue order interleaves accumulators.
-    const uint32_t tS0 = tmem_base, tC0 = tmem_base + 128;
+    const uint32_t tS0 = tmem_base, tC0 = tmem_base + 32 * n_acc;
+    constexpr int C_BUF = 16 * n_acc;  // columns of one context buffer
     pdl_wait();  // the prologue above overlapped the previous kernel (programmatic dependent launch)
 
     if (warp == 4) {
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                         if (a == 0) XA_STAMP(0, g, 0);
                         uint64_t *bar = &enc_full[s * XA_MAX_ATOMS + a];
                         ptx::mbar_expect_tx(bar, ATOM_BYTES);
-                        ptx::tma_load_3d(sEnc + s * stage_bytes + a * ATOM_BYTES, &P.enc_map, bar, a * 64, j * 128, b);
+                        ptx::tma_load_3d(sEnc + s * stage_bytes + a * ATOM_BYTES, &P.enc_map, bar, a * 64, j * KEYS, b);
                     }
                 }
             }
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
     } else if (warp == 5) {
         // ===== MMA issuer 1: scores =====
         if (lane == 0) {
-            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 16, 0, 0);  // enc (K-major) x Q' (K-major)
+            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(KEYS, 16, 0, 0);  // enc (K-major) x Q' (K-major)
             uint64_t a_desc0[2], b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
             for (int s = 0; s < 2; s++) a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), 1, 64);
             int g = 0, ci = 0;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
             int g = 0, ci = 0;
             for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
                 ptx::mbar_wait(&c_empty[ci & 1], ((ci >> 1) & 1) ^ 1);  // epilogue of chunk ci - 2 has drained this buffer
-                const uint32_t tC = tC0 + (ci & 1) * 128;
+                const uint32_t tC = tC0 + (ci & 1) * C_BUF;
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
                     ptx::mbar_wait(p_full, g & 1);  // softmax(g) done => scores(g) done reading the stage too
@@ -198,8 +205,8 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
 #pragma unroll
                     for (int m = 0; m < n_acc; m++) {  // atom pair m = channels [128 m, 128 m + 128)
 #pragma unroll
-                        for (int k = 0; k < 8; k++)
-                            ptx::mma_bf16_ss(tC + 32 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
+                        for (int k = 0; k < KEYS / 16; k++)
+                            ptx::mma_bf16_ss(tC + 16 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
                                              p_desc0 + (k >> 2) * (QATOM_BYTES >> 4) + 2 * (k & 3), idesc_c, (j | k) != 0);
                         ptx::mma_commit(&enc_empty[s * (XA_MAX_ATOMS / 2) + m]);
                     }
@@ -210,9 +217,11 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         }
     } else {
         // ===== softmax / correction / epilogue warps =====
-        const int row = warp * 32 + lane;  // key within the block, and channel lane for C
+        const int row = warp * 32 + lane;  // TMEM lane: channel lane for C, and (KEYS = 128) the key within the block
+        const bool owns_key = KEYS == 128 || lane < 16;            // M = 64 accumulators: 16 rows per warp
+        const int key = KEYS == 128 ? row : warp * 16 + lane;      // key within the block of this thread
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        for (int i = row; i < 2 * QATOM_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = row; i < (KEYS / 64) * QATOM_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0, 0, 0, 0);
         ptx::fence_proxy_async_smem();
         named_bar_sync(2, 128);
         // chunk epilogue: l[h] = sum over the 128 threads; ctx = C / l.  Deferred: it runs after the softmax of the
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
             __nv_bfloat16 *dst = P.ctx + (size_t)b_out * H * D;
             for (int m = 0; m < n_acc; m++) {
                 uint32_t cv[16];
-                tmem_ld_32x32b_x16(tC + 32 * m + lane_addr, cv);
+                tmem_ld_32x32b_x16(tC + 16 * m + lane_addr, cv);
                 ptx::tmem_ld_wait();
                 const int c = m * 128 + row;
 #pragma unroll
@@ -251,26 +260,26 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         float l_prev[H];
         for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
             float m_run[H], l_part[H];
-            const uint32_t tC = tC0 + (ci & 1) * 128;
+            const uint32_t tC = tC0 + (ci & 1) * C_BUF;
 #pragma unroll
             for (int h = 0; h < H; h++) m_run[h] = -INFINITY, l_part[h] = 0.f;
             for (int j = 0; j < nblk; j++, g++) {
                 const int s = g & 1;
-                const bool valid = j * 128 + row < P.S;
+                const bool valid = owns_key && j * KEYS + key < P.S;
                 ptx::mbar_wait(&s_full[s], (g >> 1) & 1);
                 if (threadIdx.x == 0) XA_STAMP(2, g, 0);
                 ptx::tc_fence_after();
-                uint32_t sv[16], sv1[16], sv2[16];
+                uint32_t sv[16], svp[n_acc > 1 ? n_acc - 1 : 1][16];  // the n_acc partial score accumulators
                 tmem_ld_32x32b_x16(tS0 + 16 * (s * n_acc) + lane_addr, sv);
-                if (n_acc > 1) tmem_ld_32x32b_x16(tS0 + 16 * (s * n_acc + 1) + lane_addr, sv1);
-                if (n_acc > 2) tmem_ld_32x32b_x16(tS0 + 16 * (s * n_acc + 2) + lane_addr, sv2);
+#pragma unroll
+                for (int pa = 1; pa < n_acc; pa++) tmem_ld_32x32b_x16(tS0 + 16 * (s * n_acc + pa) + lane_addr, svp[pa - 1]);
                 ptx::tmem_ld_wait();
                 if (threadIdx.x == 0) XA_STAMP(2, g, 4);
 #pragma unroll
                 for (int h = 0; h < H; h++) {
                     float v = __uint_as_float(sv[h]);
-                    if (n_acc > 1) v += __uint_as_float(sv1[h]);
-                    if (n_acc > 2) v += __uint_as_float(sv2[h]);
+#pragma unroll
+                    for (int pa = 1; pa < n_acc; pa++) v += __uint_as_float(svp[pa - 1][h]);
                     sv[h] = __float_as_uint(v);
                 }
                 ptx::tc_fence_before();
@@ -311,25 +320,26 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 if (g > 0) ptx::mbar_wait(c_done, (g - 1) & 1);  // previous block's C MMAs done: sP free, C stable
                 if (threadIdx.x == 0) XA_STAMP(2, g, 2);
                 {
-                    uint8_t *atom = sP + (row >> 6) * QATOM_BYTES;
-                    const int kk = row & 63;
+                    uint8_t *atom = sP + (key >> 6) * QATOM_BYTES;
+                    const int kk = key & 63;
 #pragma unroll
                     for (int h = 0; h < H; h++) {  // rows of the padded heads (h >= H) were zeroed once at kernel start
                         float p = valid ? exp2f(sc[h] - m_run[h]) : 0.f;
                         l_part[h] = l_part[h] * alpha[h] + p;
-                        *reinterpret_cast<__nv_bfloat16 *>(atom + h * 128 + (((kk >> 3) ^ (h & 7)) << 4) + (kk & 7) * 2) =
-                            __float2bfloat16(p);
+                        if (owns_key)
+                            *reinterpret_cast<__nv_bfloat16 *>(atom + h * 128 + (((kk >> 3) ^ (h & 7)) << 4) + (kk & 7) * 2) =
+                                __float2bfloat16(p);
                     }
                 }
                 // rescale the running context when a head's maximum moved (uniform across the CTA)
                 if (j > 0 && moved) {
                     for (int m = 0; m < n_acc; m++) {
                         uint32_t cv[16];
-                        tmem_ld_32x32b_x16(tC + 32 * m + lane_addr, cv);
+                        tmem_ld_32x32b_x16(tC + 16 * m + lane_addr, cv);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int h = 0; h < H; h++) cv[h] = __float_as_uint(__uint_as_float(cv[h]) * alpha[h]);
-                        tmem_st_32x32b_x16(tC + 32 * m + lane_addr, cv);
+                        tmem_st_32x32b_x16(tC + 16 * m + lane_addr, cv);
                     }
                     ptx::tmem_st_wait();
                 }
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 if (lane == 0) ptx::mbar_arrive(p_full);
                 if (threadIdx.x == 0) XA_STAMP(2, g, 3);
                 if (j == 0 && b_prev >= 0) {  // previous chunk: its last context MMA completed before this block's P store
-                    epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * 128);
+                    epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * C_BUF);
                     if (lane == 0) ptx::mbar_arrive(&c_empty[(ci - 1) & 1]);
                     b_prev = -1;
                 }
@@ -351,7 +361,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         }
         if (b_prev >= 0) {  // last chunk of this CTA
             ptx::mbar_wait(c_done, (g - 1) & 1);
-            epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * 128);
+            epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * C_BUF);
             if (lane == 0) ptx::mbar_arrive(&c_empty[(ci - 1) & 1]);
         }
     }
@@ -362,11 +372,12 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
 
 size_t cross_attn_absorbed_smem(int D) {
     const int atoms = D / 64;
-    return 1024 + (size_t)2 * atoms * ATOM_BYTES + XA_MAX_ATOMS * QATOM_BYTES + 2 * QATOM_BYTES +
-           (3 * XA_MAX_ATOMS + 13) * 8 + 64 * 4 + 64;
+    const int keys = xa_keys(atoms);
+    return 1024 + (size_t)2 * atoms * keys * 64 * 2 + atoms * QATOM_BYTES + (keys / 64) * QATOM_BYTES +
+           (3 * atoms + 13) * 8 + 64 * 4 + 64;
 }
 
-bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 384 && H <= 16; }
+bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 768 && H <= 16; }
 
 // q' bf16 [B][H*D] (already scaled by log2(e)/8 through the folded weights), enc bf16 [B][S][D]
 // -> ctx bf16 [B][H*D] with ctx[b][h] = softmax_j(q'_h . enc_j) weighted sum of enc_j.
@@ -376,18 +387,19 @@ int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __n
                              int B, int S, int D, int H) {
     if (B <= 0) return WB_OK;
     WB_ARG(cross_attn_absorbed_supported(D, H) && H * 64 == D,
-           "absorbed cross-attention needs head_dim 64, D %% 128 == 0, D <= 384 (D=%d H=%d)", D, H);
+           "absorbed cross-attention needs head_dim 64, D %% 128 == 0, D <= 768 (D=%d H=%d)", D, H);
     CrossAttnParams P;
-    WB_CHECK(make_tmap_bf16(&P.enc_map, enc, (uint64_t)D, (uint64_t)S, (uint64_t)B, (uint64_t)D, (uint64_t)S * D, 128, 3));
+    const int keys = xa_keys(D / 64);
+    WB_CHECK(make_tmap_bf16(&P.enc_map, enc, (uint64_t)D, (uint64_t)S, (uint64_t)B, (uint64_t)D, (uint64_t)S * D, keys, 3));
     WB_CHECK(make_tmap_bf16(&P.q_map, qp, (uint64_t)D, (uint64_t)H, (uint64_t)B, (uint64_t)D, (uint64_t)H * D, 16, 3));
-    P.ctx = ctx, P.B = B, P.S = S, P.D = D, P.H = H, P.n_blocks = cdiv(S, 128), P.atoms = D / 64;
+    P.ctx = ctx, P.B = B, P.S = S, P.D = D, P.H = H, P.n_blocks = cdiv(S, keys), P.atoms = D / 64;
     P.dbg = g_xa_dbg;
     const size_t smem = cross_attn_absorbed_smem(D);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = B < sms ? B : sms;
-    static bool opted[3] = {false, false, false};
+    static bool opted[6] = {false, false, false, false, false, false};
     auto launch = [&](auto kernel, int slot) {
         if (!opted[slot]) {
             WB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -400,7 +412,10 @@ int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __n
     switch (P.atoms) {
         case 2: return launch(cross_attn_absorbed_kernel<2>, 0);
         case 4: return launch(cross_attn_absorbed_kernel<4>, 1);
-        default: return launch(cross_attn_absorbed_kernel<6>, 2);
+        case 6: return launch(cross_attn_absorbed_kernel<6>, 2);
+        case 8: return launch(cross_attn_absorbed_kernel<8>, 3);
+        case 10: return launch(cross_attn_absorbed_kernel<10>, 4);
+        default: return launch(cross_attn_absorbed_kernel<12>, 5);
     }
 }
 

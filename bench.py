@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=2048, help="30 s chunks per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-chunks", type=int, default=4, help="chunks per CPU-baseline sample")
+    ap.add_argument("--cpu-chunks", type=int, default=16, help="chunks per CPU-baseline sample (about 10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lanes", type=int, default=1, help="decode lanes (2 = two half-batches on two streams)")

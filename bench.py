@@ -78,12 +78,28 @@ def cpu_transcribe_rate(n_chunks: int, repeats: int = 1):
     return n_chunks * CHUNK_SECONDS / best, best, O.num_threads(), n_tok
 
 
+def hf_generate_baseline():
+    """benchmark_python.py analogue (CPU baseline 3): HF `model.generate` on the host cores, one chunk."""
+    try:
+        from oracle import hf_crosscheck as H
+        from whisper_mojo_b200 import WhisperConfig, synth
+
+        cfg = WhisperConfig.tiny()
+        dt, threads = H.hf_generate_rate(cfg, synth.make_weights(cfg, seed=0), synth.make_mel(1, cfg, 0)[0], 4 + cfg.max_iters - 3)
+        return {"value": CHUNK_SECONDS / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "HF transformers WhisperForConditionalGeneration.generate (the reference's benchmark_python.py:25-30: "
+                          f"1 warm-up + 1 timed call), same random weights, 1 chunk, 196 decoder forwards, {dt:.2f} s"}
+    except Exception as ex:
+        return {"error": str(ex)[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     for _ in range(max(args.warmup, 0)):
         pass  # the CPU arm warms up inside cpu_transcribe_rate (one untimed transcribe per step)
+    hf = hf_generate_baseline()  # before the OpenMP port: its spinning worker threads would slow torch's down
     times, rate = [], 0.0
     cores = 1
     for _ in range(max(args.steps, 1)):
@@ -102,6 +118,7 @@ def run_reference(args):
                                     "Mach-O arm64 and no Mojo toolchain exists in this image"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline_hf_generate": hf,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -391,8 +408,9 @@ def run_b200(args):
     except Exception as ex:
         phase_roof = {"error": str(ex)}
 
-    cpu = None
+    cpu = cpu_hf = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_hf = hf_generate_baseline()
         rate, dt, cores, _ = cpu_transcribe_rate(args.cpu_chunks)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{args.cpu_chunks} of the same synthetic-weight 30 s chunks, batch 1, precomputed log-mel "
@@ -411,7 +429,7 @@ def run_b200(args):
                        "parallelism": f"chunks sharded x{world}, no data-path collective, final NCCL all_gather of ids",
                        "mean_tokens_per_chunk": mean_len},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "phase_rooflines": phase_roof,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "cpu_baseline_hf_generate": cpu_hf,
             "phases_ms_per_step": phases, "device_ms_each_step": step_ms, "decode_ms_each_step": step_decode_ms,
         }
         print(json.dumps(line), file=json_out, flush=True)

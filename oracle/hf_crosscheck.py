@@ -129,3 +129,26 @@ def hf_greedy(model, cfg, enc_out: np.ndarray, pos_quirk: int, max_iters: int) -
         if nxt == cfg.eot:
             break
     return np.array(toks, np.int32)
+
+
+def hf_generate_rate(cfg, flat: np.ndarray, mel: np.ndarray, n_new: int = 196):
+    """The reference's second CPU program, benchmark_python.py:8-30, restated for assets that exist here:
+    HF `WhisperForConditionalGeneration` (built from a config, same flat weights, HF's own erf GELU and
+    KV-cached `model.generate`, greedy, exactly `n_new` new tokens: EOS suppressed so the work is the same
+    196 decoder forwards the GPU path runs) on one [n_mels, n_frames] chunk, one warm-up + one timed call.
+    Returns (seconds, torch threads).  CPU baseline only: never on the product path."""
+    import time
+    from transformers.utils import logging as hf_logging
+
+    hf_logging.set_verbosity_error()
+    model = build_hf(cfg, flat, activation="gelu")
+    x = torch.from_numpy(np.ascontiguousarray(mel, np.float32))[None]
+    prompt = torch.as_tensor([list(cfg.prompt)], dtype=torch.long)
+    kw = dict(decoder_input_ids=prompt, max_new_tokens=n_new, min_new_tokens=n_new, do_sample=False, num_beams=1)
+    with torch.no_grad():
+        model.generate(input_features=x, **kw)  # warm-up, benchmark_python.py:25-26
+        t0 = time.perf_counter()
+        out = model.generate(input_features=x, **kw)
+        dt = time.perf_counter() - t0
+    assert out.shape[1] >= n_new, out.shape
+    return dt, torch.get_num_threads()

@@ -54,6 +54,28 @@ def make_weights(cfg: WhisperConfig, seed: int = 0, lin_scale: float = 1.5, emb_
     return flat
 
 
+def make_weights_hf_init(cfg: WhisperConfig, seed: int = 0, std: float = 0.02) -> np.ndarray:
+    """HF `_init_weights` statistics: linear / conv / embedding weights ~ N(0, 0.02), biases 0,
+    LayerNorm 1 / 0, sinusoidal encoder positions.  Used for the encoder-only tolerance check: activations stay small,
+    so this is the init under which north_star's 1e-2 bound is meant to be read."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for name, shape in cfg.weight_layout():
+        n = int(np.prod(shape))
+        if name == "enc.pos":
+            w = sinusoids(shape[0], shape[1]).reshape(-1)
+        elif name.endswith("ln.w") or name.endswith("ln_post.w"):
+            w = np.ones(n, np.float32)
+        elif name.endswith(".b"):
+            w = np.zeros(n, np.float32)
+        else:
+            w = rng.standard_normal(n, dtype=np.float32) * np.float32(std)
+        parts.append(w)
+    flat = np.concatenate(parts)
+    assert flat.size == cfg.weight_count()
+    return flat
+
+
 def write_weights(path: str, flat: np.ndarray) -> None:
     flat.astype("<f4", copy=False).tofile(path)
 

@@ -83,3 +83,20 @@ def test_bad_handles_are_rejected():
     assert "bad tensor handle" in _lib.last_error()
     assert lib.wm_destroy(987654) == _lib.WB_ERR_ARG
     assert lib.wt_tensor_free(0) == _lib.WB_OK
+
+
+def test_cpp_driver_links_against_the_abi_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/main.cpp is main.mojo (main.mojo:11-45) over the C ABI in plain C++: it must build with g++ alone,
+    need nothing but the library + libcudart at run time, and -- with no device -- stop at wm_create with the
+    library's error text instead of producing ids some other way."""
+    import torch
+
+    from whisper_mojo_b200 import build as B
+
+    exe = B.build_example()
+    needed = subprocess.check_output(["readelf", "-d", exe], text=True)
+    assert "libwhisper_b200.so" in needed and "torch" not in needed and "python" not in needed
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run is covered by the gpu test")
+    r = subprocess.run([exe, str(tmp_path / "missing.bin")], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and "Token IDs" not in r.stdout

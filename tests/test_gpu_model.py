@@ -371,3 +371,44 @@ def test_config3_hf_init_weights_encoder_tolerance():
     err = np.abs(enc - ref)
     print(f"hf-init enc_out: max-abs {err.max():.3e} mean-abs {err.mean():.3e} (range {np.abs(ref).max():.2f})")
     assert err.max() <= 2e-2 and err.mean() <= 3e-3, (err.max(), err.mean())
+
+
+def test_cpp_driver_prints_the_same_ids_as_the_python_mirror(tmp_path):
+    """main.mojo's twin in C++ (examples/main.cpp, C ABI only, no Python in the process): reads the reference's
+    file formats (flat fp32 weights, sample_input.bin = f32[80, 3000], vocab.txt) and must print the ids that
+    Whisper.transcribe returns; `--pcm --chunks 3` goes through wm_transcribe_pcm as a batch."""
+    import subprocess
+
+    from whisper_mojo_b200 import build as B
+
+    cfg = WhisperConfig.tiny()
+    m, w = build(cfg)
+    mel = synth.make_mel(1, cfg, 3)
+    pcm = synth.make_audio(1, cfg, 3)
+    synth.write_weights(str(tmp_path / "whisper_tiny_weights.bin"), w)
+    mel[0].astype("<f4").tofile(tmp_path / "sample_input.bin")
+    pcm[0].astype("<f4").tofile(tmp_path / "pcm.bin")
+    (tmp_path / "vocab.txt").write_text("\n".join(f"Ġw{i}" if i < 50257 else f"<|s{i}|>" for i in range(cfg.vocab_size)),
+                                        encoding="utf-8")
+    exe = B.build_example()
+
+    def ids_of(args):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, cwd=tmp_path, timeout=600)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.split("\n")
+        return [int(t) for t in lines[lines.index("Token IDs:") + 1].split()], r.stdout
+
+    got, out = ids_of([])  # main.mojo's default file names in the working directory
+    want = m.transcribe(mel[0])
+    assert got == list(want)
+    text = Tokenizer_decode(tmp_path / "vocab.txt", want)
+    assert text in out
+    got_pcm, _ = ids_of(["whisper_tiny_weights.bin", "pcm.bin", "vocab.txt", "--pcm", "--chunks", "3"])
+    toks, lens = m.transcribe_pcm_batch(pcm)
+    assert got_pcm == list(toks[0, :lens[0]])
+
+
+def Tokenizer_decode(path, ids):
+    from whisper_mojo_b200.tokenizer import Tokenizer
+
+    return Tokenizer(str(path)).decode([int(t) for t in ids])

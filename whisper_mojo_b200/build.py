@@ -67,5 +67,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_example(force: bool = False) -> str:
+    """examples/main.cpp (the reference's main.mojo over the C ABI, plain C++) -> examples/main_b200."""
+    root = os.path.dirname(HERE)
+    src, out = os.path.join(root, "examples", "main.cpp"), os.path.join(root, "examples", "main_b200")
+    hdr = os.path.join(root, "include", "whisper_b200.h")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest([src, hdr, build()]):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(root, "include"), src, "-L" + HERE, "-lwhisper_b200",
+           "-Wl,-rpath,$ORIGIN/../whisper_mojo_b200", "-Wl,--allow-shlib-undefined", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("example build failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_example(force="--force" in sys.argv))

@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=2048, help="30 s chunks per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="tiny", choices=["tiny", "small"],
+                    help="tiny = BASELINE.json configs[3] (the bench line); small = configs[4], Small-shaped 12 layers d 768")
     ap.add_argument("--cpu-chunks", type=int, default=16, help="chunks per CPU-baseline sample (about 10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -57,13 +59,13 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm on host cores (oracle port)
 # ---------------------------------------------------------------------------------------------
-def cpu_transcribe_rate(n_chunks: int, repeats: int = 1):
+def cpu_transcribe_rate(n_chunks: int, repeats: int = 1, small: bool = False):
     """audio-s/s of the CPU restatement (all host threads via OpenMP), batch 1 like the reference."""
     from oracle import oracle as O
     from whisper_mojo_b200 import WhisperConfig, synth
 
-    cfg = WhisperConfig.tiny()
-    w = synth.make_weights(cfg, seed=0)
+    cfg = WhisperConfig.small_shaped() if small else WhisperConfig.tiny()
+    w = synth.make_weights(cfg, seed=1 if small else 0)
     mel = synth.make_mel(n_chunks, cfg, 0)
     om = O.OracleWhisper(cfg, w)
     om.transcribe(mel[0])  # warm-up (mirrors benchmark_python.py:25-26)
@@ -266,11 +268,12 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = WhisperConfig.tiny()
+    small = args.model == "small"
+    cfg = WhisperConfig.small_shaped() if small else WhisperConfig.tiny()
     C = args.chunks
     stream = torch.cuda.current_stream()
     model = Whisper(cfg, stream=stream.cuda_stream)
-    model.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
+    model.load(WeightLoader(data=synth.make_weights(cfg, seed=1 if small else 0)))
     if args.lanes != 1:
         model.set_option("decode_lanes", args.lanes)
     pcm = synth_pcm_gpu(C, cfg.n_samples, dev, seed=1234 + rank)  # 3.9 GB at C=2048: larger than the 126 MB L2
@@ -367,7 +370,7 @@ def run_b200(args):
             roofline = {"bound": "hbm", "kernel": "cross_attn_absorbed_kernel (cross-attention of one layer, one decode step)",
                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s",
-                        "traffic": ncu_traffic(C), "avg_launch_ms": avg_ms, "launches_timed": n_launch,
+                        "traffic": None if small else ncu_traffic(C), "avg_launch_ms": avg_ms, "launches_timed": n_launch,
                         "algorithmic_bytes_per_launch": alg,
                         "share_of_decode": tot_ms / max(model.last_timing()["decode_ms"], 1e-9)}
     except Exception as ex:  # never lose the headline number to the profiling pass
@@ -410,21 +413,24 @@ def run_b200(args):
 
     cpu = cpu_hf = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_hf = hf_generate_baseline()
-        rate, dt, cores, _ = cpu_transcribe_rate(args.cpu_chunks)
+        cpu_hf = None if small else hf_generate_baseline()
+        n_cpu = 1 if small else args.cpu_chunks
+        rate, dt, cores, _ = cpu_transcribe_rate(n_cpu, small=small)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_chunks} of the same synthetic-weight 30 s chunks, batch 1, precomputed log-mel "
+               "sample": f"{n_cpu} of the same synthetic-weight 30 s chunks, batch 1, precomputed log-mel "
                          f"(reference's timed region), {dt:.1f} s of CPU work"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC.replace("tiny", "small_shaped") if small else METRIC, "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "whisper-tiny batched greedy transcription (BASELINE.json configs[3]): "
+            "config": {"workload": ("whisper-small-shaped (12 layers, d 768, 12 heads) batched greedy transcription "
+                                    "(BASELINE.json configs[4]): " if small else
+                                    "whisper-tiny batched greedy transcription (BASELINE.json configs[3]): ") +
                                    f"{C} synthetic 30 s chunks per GPU per step, pcm -> log-mel -> encoder -> "
                                    "196 decoder forwards (EOT never fires with random weights)",
-                       "chunks_per_gpu": C, "global_chunks": n_total, "weights": "random-init whisper-tiny shapes, seed 0",
+                       "chunks_per_gpu": C, "global_chunks": n_total, "weights": "random-init whisper-%s shapes" % ("small" if small else "tiny"),
                        "l2": "inputs (pcm %.1f GB per GPU) larger than the 126 MB L2; no explicit flush" % (pcm.numel() * 4 / 1e9),
                        "parallelism": f"chunks sharded x{world}, no data-path collective, final NCCL all_gather of ids",
                        "mean_tokens_per_chunk": mean_len},

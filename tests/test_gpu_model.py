@@ -357,9 +357,9 @@ def test_config2_frontend_one_hour_of_audio():
 
 def test_config3_hf_init_weights_encoder_tolerance():
     """SURVEY 8d config 3 names HF-init weights (N(0, 0.02), LayerNorm 1 / 0, zero biases) for the encoder-only
-    parity.  With those statistics the fp32 oracle moves by 8.4e-3 when only the weights are rounded to bf16 (measured
-    on CPU), so the bf16 path is held to max-abs <= 2e-2, mean-abs <= 3e-3 here (north_star asks 1e-2; the measured
-    value is printed and recorded in DESIGN.md)."""
+    parity, and north_star asks max-abs <= 1e-2 there.  With those statistics the fp32 oracle itself moves by 8.4e-3
+    when only the weights are rounded to bf16 (measured on CPU); the bf16 path measures 8.9e-3 max-abs, 1.3e-3
+    mean-abs on a B200 (deterministic kernels), so it is held to north_star's 1e-2 / 2e-3 here."""
     cfg = WhisperConfig.tiny()
     w = synth.make_weights_hf_init(cfg, seed=0)
     m = Whisper(cfg)
@@ -370,7 +370,7 @@ def test_config3_hf_init_weights_encoder_tolerance():
     ref = np.stack([om.encode(mel[i]) for i in range(2)])
     err = np.abs(enc - ref)
     print(f"hf-init enc_out: max-abs {err.max():.3e} mean-abs {err.mean():.3e} (range {np.abs(ref).max():.2f})")
-    assert err.max() <= 2e-2 and err.mean() <= 3e-3, (err.max(), err.mean())
+    assert err.max() <= 1e-2 and err.mean() <= 2e-3, (err.max(), err.mean())
 
 
 def test_cpp_driver_prints_the_same_ids_as_the_python_mirror(tmp_path):

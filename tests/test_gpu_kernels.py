@@ -148,11 +148,13 @@ def test_encoder_attention_tc_vs_fp64(B, S, H):
 
 
 @pytest.mark.parametrize("B,S,D,H", [(3, 1500, 384, 6), (1, 96, 128, 2), (2, 128, 128, 2), (5, 129, 256, 4), (300, 200, 384, 6),
-                                     (2, 1, 128, 2), (3, 1500, 768, 12), (2, 65, 512, 8), (160, 130, 640, 10), (1, 1, 768, 12)])
+                                     (2, 1, 128, 2), (3, 1500, 768, 12), (2, 65, 512, 8), (160, 130, 640, 10), (1, 1, 768, 12),
+                                     (170, 260, 768, 12), (151, 129, 512, 8)])
 def test_cross_attention_absorbed_vs_fp64(B, S, D, H):
     """ctx[b][h] = sum_j softmax2_j(q'_h . enc_j) enc_j (base-2 softmax: log2(e)/8 is folded into q');
-    covers the ragged last key block, a single block, more chunks than SMs, S = 1, and the 64-key-block form
-    used for d_model 512..768 (M = 64 score accumulators)."""
+    covers the ragged last key block, a single block, more chunks than SMs, S = 1, the 64-key-block form (M = 64
+    score accumulators, d_model 640) and the CTA-pair form of d_model 512 / 768 (two CTAs per chunk swap partial
+    scores through distributed shared memory), there also with more chunks than clusters and several key blocks."""
     qp = bf16_round(rng.standard_normal((B, H * D), dtype=np.float32) * 0.15)
     enc = bf16_round(rng.standard_normal((B, S, D), dtype=np.float32))
     out = debug_cross_attention_absorbed(qp, enc, H)

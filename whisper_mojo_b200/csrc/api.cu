@@ -855,6 +855,10 @@ int wb_debug_cross_attention_absorbed(const float *qp_host, const float *enc_hos
             for (int e = 0; e < 4; e++) fprintf(stderr, " %8.2f", (h[(1 * 64 + g) * 8 + e] - t0) / 1e3);
             fprintf(stderr, " |");
             for (int e = 0; e < 8; e++) fprintf(stderr, " %8.2f", (h[(2 * 64 + g) * 8 + order[e]] - t0) / 1e3);
+            if (h[(1 * 64 + g) * 8 + 4]) {  // CTA-pair form: partial scores stored to the peer / arrive issued / peer's row arrived
+                fprintf(stderr, " | xchg:");
+                for (int e = 4; e < 7; e++) fprintf(stderr, " %8.2f", (h[(1 * 64 + g) * 8 + e] - t0) / 1e3);
+            }
             fprintf(stderr, "\n");
         }
         cudaFree(d);

@@ -20,6 +20,9 @@
 // Scores arrive already multiplied by log2(e)/8 (folded into Wqk), so p = exp2(s - m).
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "sm100.cuh"
@@ -70,8 +73,43 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
         if (P.dbg && blockIdx.x == 0 && (blk) < 64) P.dbg[((role)*64 + (blk)) * 8 + (ev)] = ptx::globaltimer_ns(); \
     } while (0)
 
-template <int ATOMS>
-__global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(const __grid_constant__ CrossAttnParams P) {
+// 16-byte store into the peer CTA's shared memory that completes 16 transaction bytes on the peer's mbarrier: data and
+// signal travel together, no cluster-scope release fence (a releasing remote arrive cost ~2 us per block, measured)
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t cluster_bar, float a, float b, float c, float d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar)
+                 : "memory");
+}
+// wait on a barrier of this CTA whose arrivals come from the peer CTA of the cluster (acquire at cluster scope, so the
+// peer's shared::cluster stores issued before its releasing arrive are visible afterwards); bounded like mbar_wait
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint64_t t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(ptx::smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spins & 0xfffu) == 0) {
+            uint64_t t = ptx::globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 10000000000ull) __trap();
+        }
+    }
+}
+
+// ATOMS: 64-channel atoms THIS CTA streams.  CL = 1: one CTA per chunk, D = 64 ATOMS.  CL = 2 (D = 512 / 768): a
+// cluster of two CTAs per chunk, each streaming its half of the channels as 128-key blocks (the per-CTA shape of
+// the D = 384 kernel: 96 KB stages, M = 128 score UMMAs, half the UMMA count per key of the single-CTA 64-key
+// variant, whose 72 small UMMAs per 96 KB at ~40-50 clocks each were the limit: tools/ubench_mma.cu).  The score of a
+// key is the sum over all channels, so per block the two CTAs swap their partial scores [128 keys x H] through
+// distributed shared memory, compute the same softmax, and each accumulates the context of its own channels.
+template <int ATOMS, int CL>
+__device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
     constexpr int KEYS = xa_keys(ATOMS);
     constexpr int ATOM_BYTES = KEYS * 64 * 2;  // [KEYS x 64 channels] bf16
     constexpr int XA_MAX_ATOMS = ATOMS;
@@ -81,24 +119,33 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
     constexpr int stage_bytes = atoms * ATOM_BYTES;
     uint8_t *sEnc = base;                                  // [2][atoms][KEYS x 64]
     uint8_t *sQ = base + 2 * stage_bytes;                  // [atoms][16 x 64]
-    uint8_t *sP = sQ + XA_MAX_ATOMS * QATOM_BYTES;         // [KEYS / 64][16 x 64]   P^T, keys 0-63 | 64-127
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + (KEYS / 64) * QATOM_BYTES);
+    uint8_t *sP = sQ + XA_MAX_ATOMS * QATOM_BYTES;         // [2][KEYS / 64][16 x 64]   P^T, keys 0-63 | 64-127
+    constexpr int P_BYTES = (KEYS / 64) * QATOM_BYTES;     // one P^T buffer; block g uses buffer g & 1
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * P_BYTES);
     // enc_full[stage][atom]: one barrier per 64-channel atom, so the score MMAs of an atom issue as soon as it has
     // landed instead of after the whole 96 KB stage (the S MMAs are issue bound: ~1 us per block otherwise sits
     // between "stage arrived" and "scores ready", and with only two stages that latency caps the HBM stream)
     // enc_empty[stage][atom pair]: the context MMAs walk the atom pairs in order and release each pair as soon as
     // its 8 MMAs are done, so the refill of the stage starts ~0.7 us before the block's last MMA retires
     uint64_t *enc_full = bars, *enc_empty = bars + 2 * XA_MAX_ATOMS, *q_full = enc_empty + XA_MAX_ATOMS, *q_empty = q_full + 1,
-             *s_full = q_empty + 1, *s_empty = s_full + 2, *p_full = s_empty + 2, *c_done = p_full + 1,
-             *c_empty = c_done + 1;  // c_empty[2]: the context accumulator is double buffered over chunks
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(c_empty + 2);
-    float *s_red = reinterpret_cast<float *>(c_empty + 3);  // [4 warps][16] cross-warp reduction scratch
+             *s_full = q_empty + 1, *s_empty = s_full + 2, *p_full = s_empty + 2, *c_done = p_full + 1,  // c_done[2]: block g commits to c_done[g & 1]
+             *c_empty = c_done + 2,  // c_empty[2]: the context accumulator is double buffered over chunks
+             *x_full = c_empty + 2;  // x_full[2] (CL = 2): the peer's partial scores of block parity g & 1 have arrived
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(x_full + 2);
+    float *s_red = reinterpret_cast<float *>(x_full + 3);  // [4 warps][16] cross-warp reduction scratch
+    // [2][KEYS][H] partial scores written by the peer CTA (CL = 2)
+    float *xchg = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(s_red + 64) + 15) & ~uintptr_t(15));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = P.n_blocks, D = P.D;
     pdl_launch_dependents();
-    constexpr int H = ATOMS;  // head_dim = 64, so H = D / 64 = number of 64-channel atoms
+    constexpr int H = ATOMS * CL;     // head_dim = 64, so H = D / 64
     constexpr int n_acc = ATOMS / 2;  // C accumulators of [128 channels x 16 heads]
+    static_assert(CL == 1 || KEYS == 128, "the cluster form streams 128-key blocks");
+    const uint32_t rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+    const int b_first = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;  // chunks walk over clusters
+    const int b_step = (int)gridDim.x / CL;
+    const int ch0 = (int)rank * ATOMS * 64;  // first channel of this CTA
 
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&P.enc_map);
@@ -112,9 +159,12 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         ptx::mbar_init(q_full, 1);
         ptx::mbar_init(q_empty, 1);
         ptx::mbar_init(p_full, 4);
-        ptx::mbar_init(c_done, 1);
+        ptx::mbar_init(&c_done[0], 1);
+        ptx::mbar_init(&c_done[1], 1);
         ptx::mbar_init(&c_empty[0], 4);
         ptx::mbar_init(&c_empty[1], 4);
+        ptx::mbar_init(&x_full[0], 1);
+        ptx::mbar_init(&x_full[1], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 5) {
@@ -122,7 +172,8 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) ptx::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     // TMEM columns: score partials S[stage][part] @ 16 * (stage * n_acc + part), then the context accumulators C_m of
@@ -138,10 +189,10 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         // ===== TMA producer =====
         if (lane == 0) {
             int g = 0, ci = 0;  // g: global block counter of this CTA, ci: chunk counter
-            for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+            for (int b = b_first; b < P.B; b += b_step, ci++) {
                 ptx::mbar_wait(q_empty, (ci & 1) ^ 1);  // score MMAs of the previous chunk are done with sQ
                 ptx::mbar_expect_tx(q_full, atoms * QATOM_BYTES);
-                for (int a = 0; a < atoms; a++) ptx::tma_load_3d(sQ + a * QATOM_BYTES, &P.q_map, q_full, a * 64, 0, b);
+                for (int a = 0; a < atoms; a++) ptx::tma_load_3d(sQ + a * QATOM_BYTES, &P.q_map, q_full, ch0 + a * 64, 0, b);
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
                     for (int a = 0; a < atoms; a++) {
@@ -149,7 +200,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                         if (a == 0) XA_STAMP(0, g, 0);
                         uint64_t *bar = &enc_full[s * XA_MAX_ATOMS + a];
                         ptx::mbar_expect_tx(bar, ATOM_BYTES);
-                        ptx::tma_load_3d(sEnc + s * stage_bytes + a * ATOM_BYTES, &P.enc_map, bar, a * 64, j * KEYS, b);
+                        ptx::tma_load_3d(sEnc + s * stage_bytes + a * ATOM_BYTES, &P.enc_map, bar, ch0 + a * 64, j * KEYS, b);
                     }
                 }
             }
@@ -161,7 +212,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
             uint64_t a_desc0[2], b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
             for (int s = 0; s < 2; s++) a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), 1, 64);
             int g = 0, ci = 0;
-            for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+            for (int b = b_first; b < P.B; b += b_step, ci++) {
                 ptx::mbar_wait(q_full, ci & 1);
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
@@ -194,7 +245,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), ATOM_BYTES >> 4, 64);
             const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sP), 1, 64);
             int g = 0, ci = 0;
-            for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+            for (int b = b_first; b < P.B; b += b_step, ci++) {
                 ptx::mbar_wait(&c_empty[ci & 1], ((ci >> 1) & 1) ^ 1);  // epilogue of chunk ci - 2 has drained this buffer
                 const uint32_t tC = tC0 + (ci & 1) * C_BUF;
                 for (int j = 0; j < nblk; j++, g++) {
@@ -207,10 +258,11 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
 #pragma unroll
                         for (int k = 0; k < KEYS / 16; k++)
                             ptx::mma_bf16_ss(tC + 16 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
-                                             p_desc0 + (k >> 2) * (QATOM_BYTES >> 4) + 2 * (k & 3), idesc_c, (j | k) != 0);
+                                             p_desc0 + (g & 1) * (P_BYTES >> 4) + (k >> 2) * (QATOM_BYTES >> 4) + 2 * (k & 3),
+                                             idesc_c, (j | k) != 0);
                         ptx::mma_commit(&enc_empty[s * (XA_MAX_ATOMS / 2) + m]);
                     }
-                    ptx::mma_commit(c_done);
+                    ptx::mma_commit(&c_done[g & 1]);
                     XA_STAMP(1, g, 3);
                 }
             }
@@ -221,7 +273,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         const bool owns_key = KEYS == 128 || lane < 16;            // M = 64 accumulators: 16 rows per warp
         const int key = KEYS == 128 ? row : warp * 16 + lane;      // key within the block of this thread
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        for (int i = row; i < (KEYS / 64) * QATOM_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = row; i < 2 * P_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0, 0, 0, 0);
         ptx::fence_proxy_async_smem();
         named_bar_sync(2, 128);
         // chunk epilogue: l[h] = sum over the 128 threads; ctx = C / l.  Deferred: it runs after the softmax of the
@@ -249,7 +301,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 uint32_t cv[16];
                 tmem_ld_32x32b_x16(tC + 16 * m + lane_addr, cv);
                 ptx::tmem_ld_wait();
-                const int c = m * 128 + row;
+                const int c = ch0 + m * 128 + row;
 #pragma unroll
                 for (int h = 0; h < H; h++) dst[(size_t)h * D + c] = __float2bfloat16(__uint_as_float(cv[h]) * inv[h]);
             }
@@ -258,7 +310,7 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
         };
         int g = 0, ci = 0, b_prev = -1;
         float l_prev[H];
-        for (int b = blockIdx.x; b < P.B; b += gridDim.x, ci++) {
+        for (int b = b_first; b < P.B; b += b_step, ci++) {
             float m_run[H], l_part[H];
             const uint32_t tC = tC0 + (ci & 1) * C_BUF;
 #pragma unroll
@@ -285,16 +337,39 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&s_empty[s]);
+                if constexpr (CL > 1) {
+                    // swap partial scores with the peer: my [key][H] row goes into the peer's buffer of parity g & 1 as
+                    // st.async stores that complete transaction bytes on the peer's barrier; wait for the peer's rows.
+                    // (buffer g & 1 is rewritten at block g + 2, which the peer reaches only after my arrive of
+                    // block g + 1, i.e. after I have read block g's row)
+                    float *mine = xchg + ((g & 1) * KEYS + key) * H;
+                    const uint32_t dst = ptx::mapa_u32(mine, rank ^ 1u), dst_bar = ptx::mapa_u32(&x_full[g & 1], rank ^ 1u);
+                    if (threadIdx.x == 0) ptx::mbar_expect_tx(&x_full[g & 1], KEYS * H * 4);  // what the peer will send me
+#pragma unroll
+                    for (int h = 0; h < H; h += 4)
+                        st_async_v4(dst + h * 4, dst_bar, __uint_as_float(sv[h]), __uint_as_float(sv[h + 1]),
+                                    __uint_as_float(sv[h + 2]), __uint_as_float(sv[h + 3]));
+                    if (threadIdx.x == 0) XA_STAMP(1, g, 4);
+                    if (threadIdx.x == 0) XA_STAMP(1, g, 5);
+                    mbar_wait_cluster(&x_full[g & 1], (g >> 1) & 1);
+                    if (threadIdx.x == 0) XA_STAMP(1, g, 6);
+#pragma unroll
+                    for (int h = 0; h < H; h += 4) {
+                        const float4 o = *reinterpret_cast<const float4 *>(mine + h);
+                        sv[h] = __float_as_uint(__uint_as_float(sv[h]) + o.x);
+                        sv[h + 1] = __float_as_uint(__uint_as_float(sv[h + 1]) + o.y);
+                        sv[h + 2] = __float_as_uint(__uint_as_float(sv[h + 2]) + o.z);
+                        sv[h + 3] = __float_as_uint(__uint_as_float(sv[h + 3]) + o.w);
+                    }
+                }
                 // per-head maximum over the 128 keys of the block: butterfly steps outermost so the H independent
                 // shuffles of a step pipeline (head-outermost compiles to 5 x H serially dependent SHFLs)
                 float sc[H], mx[H];
 #pragma unroll
                 for (int h = 0; h < H; h++) mx[h] = sc[h] = valid ? __uint_as_float(sv[h]) : -INFINITY;
+                // warp maximum per head: one CREDUX.MAX.F32 each (sm_100a) instead of a 5-step shuffle butterfly
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int h = 0; h < H; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
-                }
+                for (int h = 0; h < H; h++) asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx[h]) : "f"(mx[h]));
                 if (lane < H) {
                     float v = mx[0];
 #pragma unroll
@@ -317,10 +392,11 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 }
                 // P^T[h][key] = exp2(s - m) in bf16, 128B-swizzled rows of 64 keys
                 if (threadIdx.x == 0) XA_STAMP(2, g, 1);
-                if (g > 0) ptx::mbar_wait(c_done, (g - 1) & 1);  // previous block's C MMAs done: sP free, C stable
+                // P^T is double buffered: block g - 2's context MMAs must be done with this buffer (they long are)
+                if (g > 1) ptx::mbar_wait(&c_done[g & 1], ((g - 2) >> 1) & 1);
                 if (threadIdx.x == 0) XA_STAMP(2, g, 2);
                 {
-                    uint8_t *atom = sP + (key >> 6) * QATOM_BYTES;
+                    uint8_t *atom = sP + (g & 1) * P_BYTES + (key >> 6) * QATOM_BYTES;
                     const int kk = key & 63;
 #pragma unroll
                     for (int h = 0; h < H; h++) {  // rows of the padded heads (h >= H) were zeroed once at kernel start
@@ -333,6 +409,8 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 }
                 // rescale the running context when a head's maximum moved (uniform across the CTA)
                 if (j > 0 && moved) {
+                    ptx::mbar_wait(&c_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // C holds every block < g
+                    ptx::tc_fence_after();
                     for (int m = 0; m < n_acc; m++) {
                         uint32_t cv[16];
                         tmem_ld_32x32b_x16(tC + 16 * m + lane_addr, cv);
@@ -349,7 +427,8 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
                 named_bar_sync(2, 128);  // all four warps are past their s_red reads before the next block writes it
                 if (lane == 0) ptx::mbar_arrive(p_full);
                 if (threadIdx.x == 0) XA_STAMP(2, g, 3);
-                if (j == 0 && b_prev >= 0) {  // previous chunk: its last context MMA completed before this block's P store
+                if (j == 0 && b_prev >= 0) {  // previous chunk: its last context MMAs (block g - 1) are long done by now
+                    ptx::mbar_wait(&c_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
                     epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * C_BUF);
                     if (lane == 0) ptx::mbar_arrive(&c_empty[(ci - 1) & 1]);
                     b_prev = -1;
@@ -360,21 +439,39 @@ __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(cons
             b_prev = b;
         }
         if (b_prev >= 0) {  // last chunk of this CTA
-            ptx::mbar_wait(c_done, (g - 1) & 1);
+            ptx::mbar_wait(&c_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             epilogue(b_prev, l_prev, tC0 + ((ci - 1) & 1) * C_BUF);
             if (lane == 0) ptx::mbar_arrive(&c_empty[(ci - 1) & 1]);
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) ptx::cluster_sync();  // the peer may still write this CTA's exchange buffer / barriers
+    else __syncthreads();
     if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+template <int ATOMS>
+__global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(const __grid_constant__ CrossAttnParams P) {
+    xa_body<ATOMS, 1>(P);
+}
+template <int ATOMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XA_THREADS, 1)
+    cross_attn_absorbed_pair_kernel(const __grid_constant__ CrossAttnParams P) {
+    xa_body<ATOMS, 2>(P);
+}
+
+// D = 512 / 768 run as CTA pairs (two CTAs per chunk, half the channels each) unless WB_XA_NO_PAIR is set
+static bool xa_use_pair(int atoms) {
+    static const bool off = getenv("WB_XA_NO_PAIR") != nullptr;
+    return !off && (atoms == 8 || atoms == 12);
+}
+
 size_t cross_attn_absorbed_smem(int D) {
-    const int atoms = D / 64;
+    const bool pair = xa_use_pair(D / 64);
+    const int atoms = pair ? D / 128 : D / 64;  // atoms per CTA
     const int keys = xa_keys(atoms);
-    return 1024 + (size_t)2 * atoms * keys * 64 * 2 + atoms * QATOM_BYTES + (keys / 64) * QATOM_BYTES +
-           (3 * atoms + 13) * 8 + 64 * 4 + 64;
+    return 1024 + (size_t)2 * atoms * keys * 64 * 2 + atoms * QATOM_BYTES + 2 * (keys / 64) * QATOM_BYTES +
+           (3 * atoms + 16) * 8 + 64 * 4 + 64 + (pair ? 2 * 128 * (D / 64) * 4 + 16 : 0);
 }
 
 bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 768 && H <= 16; }
@@ -389,7 +486,8 @@ int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __n
     WB_ARG(cross_attn_absorbed_supported(D, H) && H * 64 == D,
            "absorbed cross-attention needs head_dim 64, D %% 128 == 0, D <= 768 (D=%d H=%d)", D, H);
     CrossAttnParams P;
-    const int keys = xa_keys(D / 64);
+    const bool pair = xa_use_pair(D / 64);
+    const int keys = xa_keys(pair ? D / 128 : D / 64);
     WB_CHECK(make_tmap_bf16(&P.enc_map, enc, (uint64_t)D, (uint64_t)S, (uint64_t)B, (uint64_t)D, (uint64_t)S * D, keys, 3));
     WB_CHECK(make_tmap_bf16(&P.q_map, qp, (uint64_t)D, (uint64_t)H, (uint64_t)B, (uint64_t)D, (uint64_t)H * D, 16, 3));
     P.ctx = ctx, P.B = B, P.S = S, P.D = D, P.H = H, P.n_blocks = cdiv(S, keys), P.atoms = D / 64;
@@ -398,8 +496,8 @@ int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __n
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = B < sms ? B : sms;
-    static bool opted[6] = {false, false, false, false, false, false};
+    const int grid = pair ? 2 * std::min(B, sms / 2) : (B < sms ? B : sms);
+    static bool opted[8] = {false, false, false, false, false, false, false, false};
     auto launch = [&](auto kernel, int slot) {
         if (!opted[slot]) {
             WB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -409,6 +507,7 @@ int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __n
         WB_LAUNCHED();
         return WB_OK;
     };
+    if (pair) return P.atoms == 8 ? launch(cross_attn_absorbed_pair_kernel<4>, 6) : launch(cross_attn_absorbed_pair_kernel<6>, 7);
     switch (P.atoms) {
         case 2: return launch(cross_attn_absorbed_kernel<2>, 0);
         case 4: return launch(cross_attn_absorbed_kernel<4>, 1);

@@ -237,7 +237,7 @@ def ncu_traffic(chunks):
     """dram__bytes_read.sum + dram__bytes_write.sum per cross-attention launch from the committed
     `ncu --set full` capture (profiles/), valid for the chunk count it was captured at (2048); else None."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_cross_attn_absorbed_ncu_full_v2.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_cross_attn_absorbed_ncu_full_v3.json")))
         if chunks == 2048 and "2048" in d["command"]:
             return d["dram_traffic_bytes_per_launch_mean"]
     except Exception:

@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-chunks", type=int, default=16, help="chunks per CPU-baseline sample (about 10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF model.generate CPU baseline (benchmark_python.py analogue)")
     ap.add_argument("--lanes", type=int, default=1, help="decode lanes (2 = two half-batches on two streams)")
     ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "none"], help="clock sampler during the timed region")
     return ap.parse_args()
@@ -101,7 +102,7 @@ def run_reference(args):
         return 0
     for _ in range(max(args.warmup, 0)):
         pass  # the CPU arm warms up inside cpu_transcribe_rate (one untimed transcribe per step)
-    hf = hf_generate_baseline()  # before the OpenMP port: its spinning worker threads would slow torch's down
+    hf = None if args.no_hf_baseline else hf_generate_baseline()  # before the OpenMP port: its spinning worker threads would slow torch's down
     times, rate = [], 0.0
     cores = 1
     for _ in range(max(args.steps, 1)):
@@ -413,7 +414,7 @@ def run_b200(args):
 
     cpu = cpu_hf = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_hf = None if small else hf_generate_baseline()
+        cpu_hf = None if (small or args.no_hf_baseline) else hf_generate_baseline()
         n_cpu = 1 if small else args.cpu_chunks
         rate, dt, cores, _ = cpu_transcribe_rate(n_cpu, small=small)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

@@ -109,3 +109,33 @@ def test_gather_tokens_world2_gloo(n_total):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm): rank 0 prints ONE JSON line carrying the bench
+    contract's keys with the CPU restatement's own value; other ranks exit 0 silently; the B200 arm refuses to run
+    without a device (no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+
+    import torch
+
+    bench = os.path.join(ROOT, "bench.py")
+    cmd = [sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-chunks", "1", "--no-hf-baseline"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+    if not torch.cuda.is_available():
+        r2 = subprocess.run([sys.executable, bench, "--steps", "1"], capture_output=True, text=True, timeout=600)
+        assert r2.returncode != 0 and "no CUDA device" in (r2.stderr + r2.stdout)

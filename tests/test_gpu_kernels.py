@@ -208,3 +208,17 @@ def test_logmel_tensor_core_frontend_ragged_frames_and_loud_tone():
     assert np.abs(got - ref).max() / (ref.max() - ref.min()) <= 1e-4
     mt.set_option("frontend_impl", 0)
     assert np.abs(mt.log_mel(tone[None]) - got).max() <= 2e-4  # the two device frontends agree
+
+
+def test_cross_attention_cta_pair_is_deterministic():
+    """The CTA-pair form swaps partial scores between two CTAs through distributed shared memory every block; a
+    protocol race (a row read before it arrived, a buffer overwritten early) would show up as run-to-run differences.
+    Several chunks per cluster, several blocks per chunk, five runs: identical bits."""
+    r = np.random.default_rng(5)
+    B, S, D, H = 222, 700, 768, 12
+    qp = bf16_round(r.standard_normal((B, H * D), dtype=np.float32) * 0.15)
+    enc = bf16_round(r.standard_normal((B, S, D), dtype=np.float32))
+    first = debug_cross_attention_absorbed(qp, enc, H)
+    assert np.isfinite(first).all()
+    for _ in range(4):
+        assert np.array_equal(debug_cross_attention_absorbed(qp, enc, H), first)

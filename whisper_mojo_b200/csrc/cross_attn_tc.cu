@@ -14,10 +14,17 @@
 //   warp 6  MMA (context): C[D x 16 heads]         += enc_blk^T (A, MN-major) x P^T (B, K-major)     N = 16
 //                     (keys are the UMMA M dimension, so the 6 heads cost N = 16, not M = 128; the 48
 //                     small MMAs per block are issue bound, hence two issuing threads in parallel)
-//   warps 0-3 softmax: thread = key; per-head max / sum across the 128 threads (shuffles + smem),
+//   warps 0-3 softmax: thread = key; per-head max across the 128 threads (CREDUX.MAX.F32 per warp + smem),
 //                     online-softmax rescale of C through tcgen05.ld/st when a head's max moved,
-//                     P^T written to swizzled smem; at the end C / l -> bf16 ctx [B][H*D]
+//                     P^T written to one of two swizzled smem buffers; at the end C / l -> bf16 ctx [B][H*D]
 // Scores arrive already multiplied by log2(e)/8 (folded into Wqk), so p = exp2(s - m).
+//
+// d_model 512 / 768 run as CTA PAIRS (cross_attn_absorbed_pair_kernel, cluster of 2): each CTA streams half of the
+// channels of the chunk in the same 128-key blocks, the two swap their partial scores per block through distributed
+// shared memory (st.async + mbarrier complete_tx) and each accumulates the context of its own channels; see xa_body.
+// Small-N UMMAs cost ~40-50 clocks each whatever M and N are (tools/ubench_mma.cu), so what this kernel pays per key
+// is the NUMBER of UMMAs: 48 per 128-key x 384-channel stage here, 72 per 64-key x 768-channel stage in the
+// single-CTA form that d_model 640 still uses.
 #include <cuda.h>
 
 #include <algorithm>

@@ -129,7 +129,9 @@ int wm_weight_tensor(wm_model m, int index, void **dev_ptr, int64_t *n_floats);
  * encoder attention, 1 = tcgen05 flash attention (default); "frontend_impl" 0 = fp32 FMA DFT, 1 = TF32x3 tensor-core
  * DFT (default); "cross_impl" 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out
  * (default when d_model <= 768 and <= 16 heads); "use_graph", "decode_lanes", "enc_batch", "wave_max", "profile_attn" (1 = time the
- * cross-attention launches, 2 = every decode kernel by category), "pdl" (programmatic dependent launch, default 0), "decode_split_k" (split-K residual GEMMs + fused residual/LayerNorm in
+ * cross-attention launches, 2 = every decode kernel by category), "pdl" (programmatic dependent launch, default 0), "small_batch" (waves of at most this many chunks use the
+ * latency-oriented decode: K/V-form cross-attention split over the SMs + programmatic dependent launch; default 0 = off,
+ * 8 is a good value for batch-1 use), "decode_split_k" (split-K residual GEMMs + fused residual/LayerNorm in
  * the decode step: 0 = off, 1 = for batches >= 512 (default), 2 = always). */
 int wm_set_option(wm_model m, const char *key, int64_t value);
 

@@ -412,3 +412,22 @@ def Tokenizer_decode(path, ids):
     from whisper_mojo_b200.tokenizer import Tokenizer
 
     return Tokenizer(str(path)).decode([int(t) for t in ids])
+
+
+def test_small_batch_latency_path_matches_oracle():
+    """Option small_batch: waves of at most that many chunks decode with the K/V-form cross-attention split over the SMs
+    and programmatic dependent launch (the batch-1 latency path).  Same parity bar as the default path, and the option
+    must not leak into larger batches (ids of a 12-chunk batch are unchanged by it)."""
+    cfg = WhisperConfig.tiny()
+    m, w = build(cfg)
+    mel = synth.make_mel(12, cfg, 9)
+    base, base_len = m.transcribe_batch(mel)
+    m.set_option("small_batch", 8)
+    om = O.OracleWhisper(cfg, w)
+    for i in range(2):
+        ids = m.transcribe(mel[i])
+        ref, margins = om.greedy(om.encode(mel[i]), margins=True)
+        ok, msg = tokens_agree_up_to_margin(np.asarray(ids), ref, margins, MARGIN_TAU)
+        assert ok, (i, msg)
+    again, again_len = m.transcribe_batch(mel)  # 12 > small_batch: the default path, bit-identical to before
+    assert np.array_equal(again, base) and np.array_equal(again_len, base_len)

@@ -416,6 +416,9 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     else if (!strcmp(key, "enc_batch")) {
         WB_ARG(value >= 1 && value <= 4096, "enc_batch out of range");
         m->enc_batch = (int)value;
+    } else if (!strcmp(key, "small_batch")) {
+        WB_ARG(value >= 0 && value <= 4096, "small_batch out of range");
+        m->small_batch = (int)value;
     } else if (!strcmp(key, "wave_max")) {
         WB_ARG(value >= 1, "wave_max out of range");
         m->wave_max = (int)value;

@@ -674,8 +674,27 @@ static int event_pool(Model *m, size_t n_plain, size_t n_timed) {
 // buffer of the same size.  The upload is then cut into encoder sub-batches and issued on the copy stream,
 // and the frontend + encoder of sub-batch i wait only for their own slice, so the PCIe transfer of the
 // following slices runs under the compute of the earlier ones (pinned host memory makes the copies async).
+static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
+                                 int32_t *out_len_dev, const float *in_host);
+
+// Small batches (option "small_batch" = largest wave treated as small, default 0 = off): kernel-count latency, not
+// bandwidth, decides there.  One CTA per chunk cannot fill the chip in the absorbed cross-attention (12 key blocks in
+// sequence, 4 x 24 us of a 370 us step at batch 1), so such waves use the K/V form with the keys split over the SMs,
+// and programmatic dependent launch for the decode-step kernels: 74 -> 57 ms per 30 s clip at batch 1.  Off by
+// default because a chunk then no longer gets bit-identical ids alone and inside a large batch (two formulations).
 int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
                      int32_t *out_len_dev, const float *in_host) {
+    const bool small = m->small_batch > 0 && n > 0 && std::min(n, m->wave_max) <= m->small_batch && m->cross_impl == 1;
+    const int saved_impl = m->cross_impl;
+    const bool saved_pdl = g_pdl;
+    if (small) m->cross_impl = 0, g_pdl = true;
+    const int rc = model_transcribe_impl(m, mel_dev, pcm_dev, n, out_tokens_dev, out_len_dev, in_host);
+    m->cross_impl = saved_impl, g_pdl = saved_pdl;
+    return rc;
+}
+
+static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
+                                 int32_t *out_len_dev, const float *in_host) {
     WB_ARG(m->loaded, "transcribe before weights are loaded");
     WB_ARG(n > 0 && (mel_dev || pcm_dev) && out_tokens_dev && out_len_dev, "transcribe: bad arguments");
     cudaStream_t st = m->stream;

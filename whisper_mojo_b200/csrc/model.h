@@ -60,7 +60,7 @@ struct Model {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
     int gemm_impl = 1, attn_impl = 1, frontend_impl = 1,  // frontend: 0 = fp32 FMA DFT, 1 = TF32x3 tensor-core DFT
-         use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048,
+         use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048, small_batch = 0,
         decode_split_k = 1,  // split-K residual GEMMs + fused residual/LayerNorm in the decode step
         decode_lanes = 1,  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
         cross_impl = 1;    // 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (D <= 384)

@@ -8,8 +8,9 @@
 //   g++ -O2 -std=c++17 -Iinclude examples/main.cpp -Lwhisper_mojo_b200 -lwhisper_b200 -Wl,-rpath,... -o examples/main
 //   examples/main [weights.bin [sample_input.bin [vocab.txt]]]      (defaults = main.mojo's file names)
 //
-// Extra (not in main.mojo): `--chunks N` transcribes N copies of the input as one batch, and `--pcm` reads
-// 480000 fp32 samples of 16 kHz audio instead of a log-mel and runs the device frontend first.
+// Extra (not in main.mojo): `--chunks N` transcribes N copies of the input as one batch, `--pcm` reads
+// 480000 fp32 samples of 16 kHz audio instead of a log-mel and runs the device frontend first, and `--low-latency`
+// selects the small-batch decode (option small_batch = 8) for one-clip-at-a-time use.
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -69,10 +70,11 @@ static std::string decode(const std::vector<std::string> &vocab, const int32_t *
 int main(int argc, char **argv) {
     std::string weights = "whisper_tiny_weights.bin", input = "sample_input.bin", vocab_path = "vocab.txt";
     int chunks = 1, pos = 0;
-    bool pcm = false;
+    bool pcm = false, low_latency = false;
     for (int i = 1; i < argc; i++) {
         if (!std::strcmp(argv[i], "--chunks") && i + 1 < argc) chunks = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--pcm")) pcm = true;
+        else if (!std::strcmp(argv[i], "--low-latency")) low_latency = true;
         else if (pos == 0) weights = argv[i], pos++;
         else if (pos == 1) input = argv[i], pos++;
         else vocab_path = argv[i], pos++;
@@ -83,6 +85,7 @@ int main(int argc, char **argv) {
     wm_config cfg = {384, 6, 4, 51865, 1500, 448, 80, {50258, 50259, 50359, 50363}, 50257, 195, 1, {0, 0}};
     wm_model model = 0;
     if (wm_create(&cfg, nullptr, &model) != 0) die("wm_create");
+    if (low_latency && wm_set_option(model, "small_batch", 8) != 0) die("wm_set_option");
 
     std::printf("Loading weights from %s...\n", weights.c_str());
     if (wm_load_weights_file(model, weights.c_str()) != 0) die("wm_load_weights_file");

@@ -12,7 +12,7 @@
  * Two levels:
  *   wt_*  op level, 1:1 with the reference's L2 routines, fp32 device tensors (Tensor
  *         whisper_tensor.mojo:10-69).  Lets layers.mojo / whisper.mojo keep orchestrating.
- *   wm_*  model level, the batched fast path: weights uploaded once, bf16 tensor-core encoder,
+ *   wm_*  model level, the batched fast path: weights uploaded once, 16-bit (fp16 by default) tensor-core encoder,
  *         KV-cached batched greedy decode, fused logits+argmax.  `Whisper.transcribe(mel)`
  *         (whisper.mojo:184) == wm_transcribe with n_chunks = 1.
  *
@@ -41,6 +41,9 @@ int wb_last_error(char *buf, size_t n);
 int wb_abi_version(void);
 /* Number of this library's kernels launched by the calling process so far (bench evidence). */
 int64_t wb_kernel_launch_count(void);
+/* 16-bit storage / tensor-core operand type this build of the library computes in: "fp16" (default build,
+ * libwhisper_b200.so: IEEE half, 11 significand bits, fp32 accumulation) or "bf16" (libwhisper_b200_bf16.so). */
+const char *wb_precision(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Op level: `Tensor` and the L2 routines                                                     */
@@ -116,7 +119,7 @@ int wm_destroy(wm_model m);
 /* Number of fp32 values the flat weight file must hold for this config (export_weights.py:19-90). */
 int64_t wm_weight_count(const wm_config *cfg);
 /* Whisper.load(WeightLoader(path)) (loader.mojo:10-27, whisper.mojo:180-182): validates the byte
- * count, uploads once, builds the device-side bf16 / fused copies. */
+ * count, uploads once, builds the device-side 16-bit / fused copies. */
 int wm_load_weights_file(wm_model m, const char *path);
 /* Same from host memory (n_floats fp32 values in file order). */
 int wm_load_weights(wm_model m, const float *host, int64_t n_floats);
@@ -191,7 +194,7 @@ int wm_last_kernel_timing(wm_model m, const char *kernel, float *total_ms, int64
 /* ------------------------------------------------------------------------------------------ */
 /* Test hook (used by tests/ only): run one GEMM of the fast path on host fp32 data.             */
 /*   A(b, m, tap*Cin + ci) = A_host[b][(m*conv_stride + tap - pad)][ci]  (zero outside [0, src_rows)) */
-/*   out f32 [batches*rows_per_batch][N]; epi: 0 store(bf16-rounded) 1 gelu(bf16-rounded)           */
+/*   out f32 [batches*rows_per_batch][N]; epi: 0 store(16-bit-rounded) 1 gelu(16-bit-rounded)        */
 /*   2 out += (out pre-filled by the caller) 3 store f32 4 argmax (logits in out, the row's argmax    */
 /*   index replaces the LAST column).  impl: 0 CUDA-core reference kernel, 1 tcgen05/TMA kernel.                */
 /* ------------------------------------------------------------------------------------------ */
@@ -200,15 +203,15 @@ int wb_debug_gemm(int impl, const float *A_host, int batches, int src_rows, int 
                   int epi, float *out_host);
 
 /* Test hook: single-query attention of one decode step (layers.mojo:186-272) on host fp32 data
- * (rounded to bf16 on the device): q [B][D], K/V [B][len][D] -> out [B][D]; D = H*64. */
+ * (rounded to the 16-bit type on the device): q [B][D], K/V [B][len][D] -> out [B][D]; D = H*64. */
 int wb_debug_decode_attention(const float *q_host, const float *K_host, const float *V_host, int B, int H, int len,
                               int splits, float *out_host);
 
-/* Test hook: encoder self-attention (layers.mojo:273-342, no mask) on host fp32 data rounded to bf16:
+/* Test hook: encoder self-attention (layers.mojo:273-342, no mask) on host fp32 data rounded to the 16-bit type:
  * qkv [B*S][3*D] (q | k | v) -> out [B*S][D].  impl: 0 CUDA-core kernel, 1 tcgen05 flash-attention kernel. */
 int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, int H, float *out_host);
 
-/* Test hook: absorbed cross-attention (cross_attn_tc.cu) on host fp32 data rounded to bf16:
+/* Test hook: absorbed cross-attention (cross_attn_tc.cu) on host fp32 data rounded to the 16-bit type:
  * qp [B][H*D] (scores are used in base 2: p = 2^(s - max)), enc [B][S][D] -> ctx [B][H*D]. */
 int wb_debug_cross_attention_absorbed(const float *qp_host, const float *enc_host, int B, int S, int D, int H,
                                       float *ctx_host);

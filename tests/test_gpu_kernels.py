@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from gpu_util import (bf16_round, debug_cross_attention_absorbed, debug_decode_attention, debug_encoder_attention,
+from gpu_util import (h16_round, debug_cross_attention_absorbed, debug_decode_attention, debug_encoder_attention,
                       debug_gemm)
 from oracle import logmel_oracle as LM
 from whisper_mojo_b200 import Whisper, WhisperConfig, synth
@@ -21,16 +21,16 @@ def test_gemm_tc_all_epilogues(M, N, K):
     A = rng.standard_normal((M, K), dtype=np.float32)
     W = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
     b = rng.standard_normal(N, dtype=np.float32)
-    ref = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T + b
+    ref = h16_round(A).astype(np.float64) @ h16_round(W).astype(np.float64).T + b
     tol = 2e-5 * max(1.0, K / 64)
     for impl in (0, 1):
         assert np.abs(debug_gemm(impl, A, W, b, 3) - ref).max() <= tol  # fp32 store: bit-level bf16 x bf16 products
-    assert np.array_equal(debug_gemm(1, A, W, b, 0), bf16_round(debug_gemm(1, A, W, b, 3)))  # bf16 store = rounded fp32
+    assert np.array_equal(debug_gemm(1, A, W, b, 0), h16_round(debug_gemm(1, A, W, b, 3)))  # bf16 store = rounded fp32
     g = torch.nn.functional.gelu(torch.from_numpy(ref), approximate="tanh").numpy()
     assert np.abs(debug_gemm(1, A, W, b, 1) - g).max() <= 2e-2  # bf16 output, |g| <~ 5
     x0 = rng.standard_normal((M, N), dtype=np.float32)
     assert np.abs(debug_gemm(1, A, W, b, 2, out0=x0) - (x0 + ref)).max() <= tol
-    lg = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
+    lg = h16_round(A).astype(np.float64) @ h16_round(W).astype(np.float64).T
     for impl in (0, 1):
         am = debug_gemm(impl, A, W, None, 4)
         assert np.array_equal(am[:, -1].astype(np.int64), lg.argmax(1))
@@ -52,7 +52,7 @@ def test_gemm_conv_taps(cs, Cin, L, N, B):
     A = rng.standard_normal((B, L, Cin), dtype=np.float32)
     W = rng.standard_normal((N, 3 * Cin), dtype=np.float32) / np.sqrt(3 * Cin)
     Lo = (L + 2 - 3) // cs + 1
-    Ab, Wb = bf16_round(A).astype(np.float64), bf16_round(W).astype(np.float64)
+    Ab, Wb = h16_round(A).astype(np.float64), h16_round(W).astype(np.float64)
     ref = np.zeros((B, Lo, N))
     for t in range(3):
         rows = np.arange(Lo) * cs + t - 1
@@ -70,17 +70,17 @@ def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
     A = rng.standard_normal((M, K), dtype=np.float32)
     W = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
     b = rng.standard_normal(N, dtype=np.float32)
-    ref = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T + b
+    ref = h16_round(A).astype(np.float64) @ h16_round(W).astype(np.float64).T + b
     tol = 2e-5 * max(1.0, K / 64)
     f32 = debug_gemm(3, A, W, b, 3)
     assert np.abs(f32 - ref).max() <= tol
     assert np.array_equal(f32, debug_gemm(2, A, W, b, 3))  # same k order as the single-CTA kernel: bit-identical
-    assert np.array_equal(debug_gemm(3, A, W, b, 0), bf16_round(f32))
+    assert np.array_equal(debug_gemm(3, A, W, b, 0), h16_round(f32))
     g = torch.nn.functional.gelu(torch.from_numpy(ref), approximate="tanh").numpy()
     assert np.abs(debug_gemm(3, A, W, b, 1) - g).max() <= 2e-2
     x0 = rng.standard_normal((M, N), dtype=np.float32)
     assert np.abs(debug_gemm(3, A, W, b, 2, out0=x0) - (x0 + ref)).max() <= tol
-    lg = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
+    lg = h16_round(A).astype(np.float64) @ h16_round(W).astype(np.float64).T
     am = debug_gemm(3, A, W, None, 4)  # fused logits + argmax partials (first maximum wins)
     assert np.array_equal(am[:, -1].astype(np.int64), lg.argmax(1))
     assert np.abs(am[:, :-1] - lg[:, :-1]).max() <= tol
@@ -95,7 +95,7 @@ def test_gemm_cta_pair_argmax_ties_and_vocab_width():
     assert np.all(debug_gemm(3, A, W, None, 4)[:, -1] == 5)
     A = rng.standard_normal((300, 384), dtype=np.float32)
     W = rng.standard_normal((51865 // 8, 384), dtype=np.float32) / 20  # ragged last tile like the real vocabulary
-    lg = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
+    lg = h16_round(A).astype(np.float64) @ h16_round(W).astype(np.float64).T
     assert np.array_equal(debug_gemm(3, A, W, None, 4)[:, -1].astype(np.int64), lg.argmax(1))
 
 
@@ -104,7 +104,7 @@ def test_gemm_cta_pair_conv_taps(cs, Cin, L, N, B):
     A = rng.standard_normal((B, L, Cin), dtype=np.float32)
     W = rng.standard_normal((N, 3 * Cin), dtype=np.float32) / np.sqrt(3 * Cin)
     Lo = (L + 2 - 3) // cs + 1
-    Ab, Wb = bf16_round(A).astype(np.float64), bf16_round(W).astype(np.float64)
+    Ab, Wb = h16_round(A).astype(np.float64), h16_round(W).astype(np.float64)
     ref = np.zeros((B, Lo, N))
     for t in range(3):
         rows = np.arange(Lo) * cs + t - 1
@@ -118,9 +118,9 @@ def test_gemm_cta_pair_conv_taps(cs, Cin, L, N, B):
                                            (2, 6, 2, 1), (2, 6, 3, 1), (2, 6, 17, 1), (2, 6, 19, 1), (1, 6, 1500, 7)])
 def test_decode_attention(B, H, ln, splits):
     D = H * 64
-    q = bf16_round(rng.standard_normal((B, D), dtype=np.float32) * 1.5)
-    K = bf16_round(rng.standard_normal((B, ln, D), dtype=np.float32) * 1.5)
-    V = bf16_round(rng.standard_normal((B, ln, D), dtype=np.float32))
+    q = h16_round(rng.standard_normal((B, D), dtype=np.float32) * 1.5)
+    K = h16_round(rng.standard_normal((B, ln, D), dtype=np.float32) * 1.5)
+    V = h16_round(rng.standard_normal((B, ln, D), dtype=np.float32))
     out = debug_decode_attention(q, K, V, H, splits)
     qh, Kh, Vh = (x.astype(np.float64) for x in (q.reshape(B, H, 64), K.reshape(B, ln, H, 64), V.reshape(B, ln, H, 64)))
     s = np.einsum("bhd,bjhd->bhj", qh, Kh) * 0.125
@@ -135,7 +135,7 @@ def test_encoder_attention_tc_vs_fp64(B, S, H):
     """tcgen05 flash attention == softmax(q k^T / 8) v on the same bf16-rounded inputs; covers a ragged
     last key block (1500 = 11*128 + 92), a single block, an exact multiple and S = 1."""
     D = H * 64
-    qkv = bf16_round(rng.standard_normal((B * S, 3 * D), dtype=np.float32) * np.array([1.5] * (2 * D) + [1.0] * D, np.float32))
+    qkv = h16_round(rng.standard_normal((B * S, 3 * D), dtype=np.float32) * np.array([1.5] * (2 * D) + [1.0] * D, np.float32))
     x = qkv.reshape(B, S, 3, H, 64).astype(np.float64)
     s = np.einsum("bihd,bjhd->bhij", x[:, :, 0], x[:, :, 1]) * 0.125
     p = np.exp(s - s.max(-1, keepdims=True))
@@ -155,8 +155,8 @@ def test_cross_attention_absorbed_vs_fp64(B, S, D, H):
     covers the ragged last key block, a single block, more chunks than SMs, S = 1, the 64-key-block form (M = 64
     score accumulators, d_model 640) and the CTA-pair form of d_model 512 / 768 (two CTAs per chunk swap partial
     scores through distributed shared memory), there also with more chunks than clusters and several key blocks."""
-    qp = bf16_round(rng.standard_normal((B, H * D), dtype=np.float32) * 0.15)
-    enc = bf16_round(rng.standard_normal((B, S, D), dtype=np.float32))
+    qp = h16_round(rng.standard_normal((B, H * D), dtype=np.float32) * 0.15)
+    enc = h16_round(rng.standard_normal((B, S, D), dtype=np.float32))
     out = debug_cross_attention_absorbed(qp, enc, H)
     q = qp.reshape(B, H, D).astype(np.float64)
     e = enc.astype(np.float64)
@@ -216,8 +216,8 @@ def test_cross_attention_cta_pair_is_deterministic():
     Several chunks per cluster, several blocks per chunk, five runs: identical bits."""
     r = np.random.default_rng(5)
     B, S, D, H = 222, 700, 768, 12
-    qp = bf16_round(r.standard_normal((B, H * D), dtype=np.float32) * 0.15)
-    enc = bf16_round(r.standard_normal((B, S, D), dtype=np.float32))
+    qp = h16_round(r.standard_normal((B, H * D), dtype=np.float32) * 0.15)
+    enc = h16_round(r.standard_normal((B, S, D), dtype=np.float32))
     first = debug_cross_attention_absorbed(qp, enc, H)
     assert np.isfinite(first).all()
     for _ in range(4):

@@ -1,25 +1,27 @@
 """GPU: model-level parity of the batched fast path against the CPU oracle on seeded inputs, plus
 the op-by-op engine, batch invariance, the step API and error behaviour.
 
-Tolerances (written here, justified in DESIGN.md "Precision"): the fast path stores weights, GEMM
-operands and the KV cache in bf16 with fp32 accumulation and an fp32 residual stream.  On these
-synthetic weights the fp32 oracle itself moves by 2.1e-2 (enc_out) / 4e-2 (logits) when only the
-weights are rounded to bf16, so the bounds below are: enc_out max-abs <= 4e-2 (mean-abs <= 6e-3),
-logits max-abs <= 1e-1 (median <= 1e-2), greedy ids identical to the oracle up to the first step whose
-fp32 top-1/top-2 margin is below 0.1.  The op-by-op engine is fp32 and is held to 1e-4 / exact ids.
+Tolerances (written in gpu_util.tolerances(), justified in DESIGN.md "Precision"): the fast path stores
+weights, GEMM operands and the KV cache in 16 bits with fp32 accumulation and an fp32 residual stream.
+Default build = fp16 operands: north_star's bound, enc_out and teacher-forced logits max-abs <= 1e-2
+(mean 1.5e-3 / median 2e-3), on the synthetic O(1)-residual weights AND on HF-init weights; greedy ids
+identical to the oracle, the only excuse for a first mismatch being an oracle top-1/top-2 margin below
+2e-2 (= 2 x the logit bound) AT the mismatching step.  (The bf16 build, WB_PRECISION=bf16, keeps round 1's
+4e-2 / 1e-1 / tau 0.1: bf16 weight rounding alone moves the fp32 oracle by 2.1e-2 / 3.9e-2 on these weights,
+tools/error_attribution.py.)  The op-by-op engine is fp32 and is held to 1e-4 / exact ids.
 """
 import numpy as np
 import pytest
 import torch
 
-from gpu_util import tokens_agree_up_to_margin
+from gpu_util import token_report, tokens_agree_up_to_margin, tolerances
 from oracle import logmel_oracle as LM
 from oracle import oracle as O
 from whisper_mojo_b200 import DeviceKVCache, Tensor, WeightLoader, Whisper, WhisperConfig, _lib, synth
 
 pytestmark = pytest.mark.gpu
 
-ENC_MAX, ENC_MEAN, LOGIT_MAX, LOGIT_MEDIAN, MARGIN_TAU = 4e-2, 6e-3, 1e-1, 1e-2, 0.1
+ENC_MAX, ENC_MEAN, LOGIT_MAX, LOGIT_MEDIAN, MARGIN_TAU = tolerances()
 
 
 def build(cfg, engine="fast", seed=0, **opts):
@@ -87,7 +89,7 @@ def test_reference_kernels_agree_with_tensor_core_kernels(setup):
     cfg, mel, m, om, enc_ref = setup
     m0, _ = build(cfg, gemm_impl=0)
     e0, e1 = m0.encode(mel[:1]), m.encode(mel[:1])
-    assert np.abs(e0 - e1).max() <= 2e-2  # same bf16 rounding points, different summation order
+    assert np.abs(e0 - e1).max() <= ENC_MAX  # same 16-bit rounding points, different summation order
     t0, l0 = m0.transcribe_batch(mel[:1])
     t1, l1 = m.transcribe_batch(mel[:1])
     ref, mg = om.greedy(enc_ref[0], margins=True)
@@ -227,7 +229,7 @@ def test_split_k_decode_path_matches_oracle(setup):
     la, lb = ms.teacher_forced(enc, forced), m0.teacher_forced(enc, forced)
     ref = np.stack([om.teacher_forced(enc_ref[i], forced[i]) for i in range(len(mel))])
     assert np.abs(la - ref).max() <= LOGIT_MAX and np.abs(lb - ref).max() <= LOGIT_MAX
-    assert np.abs(la - lb).max() <= LOGIT_MAX / 2
+    assert np.abs(la - lb).max() <= LOGIT_MAX
 
 
 def test_two_decode_lanes_equal_one_lane():
@@ -355,11 +357,11 @@ def test_config2_frontend_one_hour_of_audio():
         assert np.abs(mel[i] - ref).max() / (ref.max() - ref.min()) <= 1e-4, i
 
 
-def test_config3_hf_init_weights_encoder_tolerance():
+def test_config3_hf_init_weights_encoder_and_logits_tolerance():
     """SURVEY 8d config 3 names HF-init weights (N(0, 0.02), LayerNorm 1 / 0, zero biases) for the encoder-only
-    parity, and north_star asks max-abs <= 1e-2 there.  With those statistics the fp32 oracle itself moves by 8.4e-3
-    when only the weights are rounded to bf16 (measured on CPU); the bf16 path measures 8.9e-3 max-abs, 1.3e-3
-    mean-abs on a B200 (deterministic kernels), so it is held to north_star's 1e-2 / 2e-3 here."""
+    parity, and north_star asks max-abs <= 1e-2 on enc_out and logits.  Held to 1e-2 in both builds (bf16 measures
+    8.9e-3 there; fp16 is predicted at 1.1e-3 / 1.5e-3 by tools/error_attribution.py), enc_out AND teacher-forced
+    logits."""
     cfg = WhisperConfig.tiny()
     w = synth.make_weights_hf_init(cfg, seed=0)
     m = Whisper(cfg)
@@ -371,6 +373,66 @@ def test_config3_hf_init_weights_encoder_tolerance():
     err = np.abs(enc - ref)
     print(f"hf-init enc_out: max-abs {err.max():.3e} mean-abs {err.mean():.3e} (range {np.abs(ref).max():.2f})")
     assert err.max() <= 1e-2 and err.mean() <= 2e-3, (err.max(), err.mean())
+    forced = np.stack([np.concatenate([np.array(cfg.prompt), np.random.default_rng(40 + i).integers(0, cfg.vocab_size, 12)])
+                       for i in range(2)]).astype(np.int32)
+    lref = np.stack([om.teacher_forced(ref[i], forced[i]) for i in range(2)])
+    lg = m.teacher_forced(torch.from_numpy(ref).cuda(), forced)
+    lerr = np.abs(lg - lref)
+    print(f"hf-init logits: max-abs {lerr.max():.3e} median {np.median(lerr):.3e} (range {np.abs(lref).max():.2f})")
+    assert lerr.max() <= 1e-2, lerr.max()
+
+
+def test_sixteen_tiny_chunks_token_exact():
+    """north_star: greedy ids bit-identical to the reference's own output on synthetic chunks.  16 Tiny chunks x 200
+    ids against the fp32 oracle: every chunk must be identical, or differ first at a step whose oracle top-1/top-2
+    margin is below tau (gpu_util.tolerances: 2 x the logit bound); the count of identical chunks is printed and, for
+    the fp16 build, at least 12 of 16 must be identical outright (oracle margins on these chunks go down to 1.3e-3,
+    below what ANY non-bit-identical fp32 summation order could resolve)."""
+    cfg = WhisperConfig.tiny()
+    m, w = build(cfg)
+    n = 16
+    mel = synth.make_mel(n, cfg, 0)
+    toks, lens = m.transcribe_batch(mel)
+    om = O.OracleWhisper(cfg, w)
+    refs, mgs = [], []
+    for i in range(n):
+        r, mg = om.greedy(om.encode(mel[i]), margins=True)
+        refs.append(r), mgs.append(mg)
+    ok, ident, text = token_report([toks[i, :lens[i]] for i in range(n)], refs, mgs, MARGIN_TAU)
+    print("tiny 16 x 200 ids:", text)
+    assert ok, text
+    if _lib.precision() == "fp16":
+        assert ident >= 12, text
+
+
+def test_config4_full_size_2048_chunks():
+    """BASELINE.json configs[3] at its full size: one wave of 2048 Tiny chunks through the regime the bench times
+    (auto split-K decode GEMMs, pair tiles, 148 persistent cross-attention CTAs, 16 encoder sub-batches).  The batch
+    is 16 distinct log-mels tiled 128 times; (a) EVERY copy of a mel must produce identical ids wherever it sits in
+    the batch (size-independent property: batch invariance over all 2048 positions), (b) 8 positions spread over the
+    batch must equal the solo run (batch 1) of their mel bit for bit, (c) the same 8 are checked against the fp32
+    oracle with the strict rule of tokens_agree_up_to_margin."""
+    cfg = WhisperConfig.tiny()
+    m, w = build(cfg)
+    n, d = 2048, 16
+    mel = synth.make_mel(d, cfg, 21)
+    mel_dev = torch.from_numpy(mel).cuda().repeat(n // d, 1, 1).contiguous()  # position p holds mel[p % 16]
+    toks, lens = m.transcribe_batch(mel_dev)
+    toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
+    del mel_dev
+    assert (lens == cfg.max_tokens).all() or (lens >= 5).all()
+    for p in range(d, n):
+        assert np.array_equal(toks[p], toks[p % d]) and lens[p] == lens[p % d], p
+    om = O.OracleWhisper(cfg, w)
+    got, refs, mgs = [], [], []
+    for p in (0, 127, 128, 777, 1023, 1024, 1500, 2047):
+        t1, l1 = m.transcribe_batch(mel[p % d][None])
+        assert np.array_equal(t1[0], toks[p]) and l1[0] == lens[p], p
+        r, mg = om.greedy(om.encode(mel[p % d]), margins=True)
+        got.append(toks[p, :lens[p]]), refs.append(r), mgs.append(mg)
+    ok, ident, text = token_report(got, refs, mgs, MARGIN_TAU)
+    print("configs[3] 2048-chunk wave, 8 positions vs oracle:", text)
+    assert ok, text
 
 
 def test_cpp_driver_prints_the_same_ids_as_the_python_mirror(tmp_path):

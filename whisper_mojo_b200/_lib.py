@@ -10,7 +10,12 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwhisper_b200.so")
+# WB_PRECISION=bf16 in the environment selects the bf16 build of the library (A/B measurements; the
+# default fp16 build is the one that meets the parity bar, see csrc/dtype.h)
+PRECISION = os.environ.get("WB_PRECISION", "fp16").lower()
+if PRECISION not in ("fp16", "bf16"):
+    raise ImportError(f"WB_PRECISION={PRECISION!r}: expected fp16 or bf16")
+LIB_PATH = os.path.join(HERE, "libwhisper_b200.so" if PRECISION == "fp16" else "libwhisper_b200_bf16.so")
 
 WB_OK, WB_ERR_ARG, WB_ERR_CUDA, WB_ERR_IO, WB_ERR_STATE = 0, 1, 2, 3, 4
 
@@ -27,6 +32,7 @@ SIGNATURES = {
     "wb_last_error": (c_int, [ctypes.c_char_p, c_size_t]),
     "wb_abi_version": (c_int, []),
     "wb_kernel_launch_count": (c_int64, []),
+    "wb_precision": (c_char_p, []),
     "wt_tensor_alloc": (c_int, [c_int64, c_int64, POINTER(c_uint64)]),
     "wt_tensor_view": (c_int, [c_uint64, c_int64, c_int64, c_int64, POINTER(c_uint64)]),
     "wt_tensor_free": (c_int, [c_uint64]),
@@ -105,6 +111,11 @@ def last_error() -> str:
 def check(rc: int) -> None:
     if rc != WB_OK:
         raise WhisperB200Error(rc, last_error())
+
+
+def precision() -> str:
+    """"fp16" or "bf16": the 16-bit operand type of the loaded library."""
+    return load().wb_precision().decode()
 
 
 def launch_count() -> int:

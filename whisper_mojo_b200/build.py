@@ -16,7 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libwhisper_b200.so")
+LIB = os.path.join(HERE, "libwhisper_b200.so")  # fp16 operands (default; csrc/dtype.h)
+LIB_BF16 = os.path.join(HERE, "libwhisper_b200_bf16.so")  # -DWB_BF16: the bf16 variant, for A/B numbers
 SOURCES = ["api.cu", "ops.cu", "gemm.cu", "kernels.cu", "frontend.cu", "frontend_tc.cu", "model.cu", "attn_tc.cu", "cross_attn_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
               "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -38,9 +39,11 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, bf16: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "whisper_b200.h")]
+    LIB = LIB_BF16 if bf16 else globals()["LIB"]
+    OBJ = globals()["OBJ"] + ("_bf16" if bf16 else "")
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest(deps):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -48,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src) + ".o")
-        cmd = [nvcc] + _host_compiler_flags() + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + _host_compiler_flags() + NVCC_FLAGS + (["-DWB_BF16"] if bf16 else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -85,4 +88,5 @@ def build_example(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bf16=True))
     print(build_example(force="--force" in sys.argv))

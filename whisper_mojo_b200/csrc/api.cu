@@ -93,6 +93,7 @@ int wb_last_error(char *buf, size_t n) {
 }
 int wb_abi_version(void) { return 1; }
 int64_t wb_kernel_launch_count(void) { return g_launches.load(); }
+const char *wb_precision(void) { return WB_H16_NAME; }
 
 // ---- op level ----------------------------------------------------------------------------------
 
@@ -615,9 +616,9 @@ int wm_last_kernel_timing(wm_model h, const char *kernel, float *total_ms, int64
 }
 
 
-static __global__ void bf16_to_f32_kernel(const __nv_bfloat16 *src, float *dst, size_t n) {
+static __global__ void h16_to_f32_kernel(const h16 *src, float *dst, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = __bfloat162float(src[i]);
+    if (i < n) dst[i] = h2f(src[i]);
 }
 
 int wb_debug_gemm(int impl, const float *A_host, int batches, int src_rows, int lda, int Cin, int taps,
@@ -630,7 +631,7 @@ int wb_debug_gemm(int impl, const float *A_host, int batches, int src_rows, int 
     const size_t M = (size_t)batches * rows_per_batch, nO = M * N;
     const int tiles_n = gemm_tiles_n(N);
     float *dA32 = nullptr, *dW32 = nullptr, *dbias = nullptr, *dout = nullptr, *dpv = nullptr;
-    __nv_bfloat16 *dA = nullptr, *dW = nullptr, *dob = nullptr;
+    h16 *dA = nullptr, *dW = nullptr, *dob = nullptr;
     int *dpi = nullptr, *dnext = nullptr;
     int rc = WB_OK;
     auto ok = [&](cudaError_t e) {
@@ -655,21 +656,21 @@ int wb_debug_gemm(int impl, const float *A_host, int batches, int src_rows, int 
         if (bias_host) ok(cudaMemcpy(dbias, bias_host, (size_t)N * 4, cudaMemcpyHostToDevice));
         ok(cudaMemcpy(dout, out_host, nO * 4, cudaMemcpyHostToDevice));
     }
-    if (rc == WB_OK) rc = convert_f32_bf16(0, dA32, dA, nA);
-    if (rc == WB_OK) rc = convert_f32_bf16(0, dW32, dW, nW);
+    if (rc == WB_OK) rc = convert_f32_h16(0, dA32, dA, nA);
+    if (rc == WB_OK) rc = convert_f32_h16(0, dW32, dW, nW);
     if (rc == WB_OK) {
         GemmDesc g;
         g.A = dA, g.a_batch_stride = (int64_t)src_rows * lda, g.lda = lda, g.src_rows = src_rows;
         g.conv_stride = conv_stride, g.pad = pad, g.taps = taps, g.Cin = Cin;
         g.batches = batches, g.rows_per_batch = rows_per_batch;
         g.W = dW, g.N = N, g.bias = bias_host ? dbias : nullptr, g.epi = epi;
-        const bool bf = (epi == EPI_STORE_BF16 || epi == EPI_GELU_BF16);
+        const bool bf = (epi == EPI_STORE_H16 || epi == EPI_GELU_H16);
         g.out[0] = bf ? (void *)dob : (void *)dout, g.out_ld[0] = N;
         if (epi == EPI_ARGMAX) g.part_val = dpv, g.part_idx = dpi, g.logits = dout, g.out[0] = nullptr;
         rc = gemm_run(0, g, impl);
         if (rc == WB_OK && epi == EPI_ARGMAX) rc = argmax_partials(0, dpv, dpi, (int)M, tiles_n, dnext);
         if (rc == WB_OK && bf) {
-            bf16_to_f32_kernel<<<(unsigned)((nO + 255) / 256), 256>>>(dob, dout, nO);
+            h16_to_f32_kernel<<<(unsigned)((nO + 255) / 256), 256>>>(dob, dout, nO);
             ok(cudaGetLastError());
         }
     }
@@ -698,7 +699,7 @@ int wb_debug_decode_attention(const float *q_host, const float *K_host, const fl
     const int D = H * 64;
     const size_t nq = (size_t)B * D, nkv = (size_t)B * len * D;
     float *f32 = nullptr, *ws = nullptr;
-    __nv_bfloat16 *q = nullptr, *K = nullptr, *V = nullptr, *o = nullptr;
+    h16 *q = nullptr, *K = nullptr, *V = nullptr, *o = nullptr;
     int *len_dev = nullptr;
     int rc = WB_OK;
     auto ok = [&](cudaError_t e) {
@@ -715,11 +716,11 @@ int wb_debug_decode_attention(const float *q_host, const float *K_host, const fl
     ok(cudaMalloc((void **)&ws, (size_t)B * splits * H * 66 * 4));
     ok(cudaMalloc((void **)&len_dev, 4));
     const float *srcs[3] = {q_host, K_host, V_host};
-    __nv_bfloat16 *dsts[3] = {q, K, V};
+    h16 *dsts[3] = {q, K, V};
     const size_t ns[3] = {nq, nkv, nkv};
     for (int i = 0; i < 3 && rc == WB_OK; i++) {
         ok(cudaMemcpy(f32, srcs[i], ns[i] * 4, cudaMemcpyHostToDevice));
-        if (rc == WB_OK) rc = convert_f32_bf16(0, f32, dsts[i], ns[i]);
+        if (rc == WB_OK) rc = convert_f32_h16(0, f32, dsts[i], ns[i]);
         ok(cudaDeviceSynchronize());
     }
     if (rc == WB_OK) {
@@ -734,7 +735,7 @@ int wb_debug_decode_attention(const float *q_host, const float *K_host, const fl
         rc = decode_attention(0, a);
     }
     if (rc == WB_OK) {
-        bf16_to_f32_kernel<<<(unsigned)((nq + 255) / 256), 256>>>(o, f32, nq);
+        h16_to_f32_kernel<<<(unsigned)((nq + 255) / 256), 256>>>(o, f32, nq);
         ok(cudaGetLastError());
         ok(cudaMemcpy(out_host, f32, nq * 4, cudaMemcpyDeviceToHost));
     }
@@ -749,7 +750,7 @@ int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, in
     const int D = H * 64;
     const size_t nin = (size_t)B * S * 3 * D, nout = (size_t)B * S * D;
     float *f32 = nullptr;
-    __nv_bfloat16 *qkv = nullptr, *o = nullptr;
+    h16 *qkv = nullptr, *o = nullptr;
     int rc = WB_OK;
     auto ok = [&](cudaError_t e) {
         if (e != cudaSuccess && rc == WB_OK) {
@@ -761,7 +762,7 @@ int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, in
     ok(cudaMalloc((void **)&qkv, nin * 2));
     ok(cudaMalloc((void **)&o, nout * 2));
     if (rc == WB_OK) ok(cudaMemcpy(f32, qkv_host, nin * 4, cudaMemcpyHostToDevice));
-    if (rc == WB_OK) rc = convert_f32_bf16(0, f32, qkv, nin);
+    if (rc == WB_OK) rc = convert_f32_h16(0, f32, qkv, nin);
     if (rc == WB_OK) rc = impl ? encoder_attention_tc(0, qkv, o, B, S, H, D) : encoder_attention_ref(0, qkv, o, B, S, H, D);
     if (rc == WB_OK && impl && getenv("WB_EA_DBG")) {  // timestamp dump of two CTAs (development aid)
         unsigned long long *d = nullptr;
@@ -800,7 +801,7 @@ int wb_debug_encoder_attention(int impl, const float *qkv_host, int B, int S, in
         cudaFree(d);
     }
     if (rc == WB_OK) {
-        bf16_to_f32_kernel<<<(unsigned)((nout + 255) / 256), 256>>>(o, f32, nout);
+        h16_to_f32_kernel<<<(unsigned)((nout + 255) / 256), 256>>>(o, f32, nout);
         ok(cudaGetLastError());
         ok(cudaMemcpy(out_host, f32, nout * 4, cudaMemcpyDeviceToHost));
     }
@@ -815,7 +816,7 @@ int wb_debug_cross_attention_absorbed(const float *qp_host, const float *enc_hos
     WB_CHECK(need_device());
     const size_t nq = (size_t)B * H * D, ne = (size_t)B * S * D;
     float *f32 = nullptr;
-    __nv_bfloat16 *qp = nullptr, *enc = nullptr, *ctx = nullptr;
+    h16 *qp = nullptr, *enc = nullptr, *ctx = nullptr;
     int rc = WB_OK;
     auto ok = [&](cudaError_t e) {
         if (e != cudaSuccess && rc == WB_OK) {
@@ -828,10 +829,10 @@ int wb_debug_cross_attention_absorbed(const float *qp_host, const float *enc_hos
     ok(cudaMalloc((void **)&enc, ne * 2));
     ok(cudaMalloc((void **)&ctx, nq * 2));
     if (rc == WB_OK) ok(cudaMemcpy(f32, qp_host, nq * 4, cudaMemcpyHostToDevice));
-    if (rc == WB_OK) rc = convert_f32_bf16(0, f32, qp, nq);
+    if (rc == WB_OK) rc = convert_f32_h16(0, f32, qp, nq);
     if (rc == WB_OK) ok(cudaDeviceSynchronize());
     if (rc == WB_OK) ok(cudaMemcpy(f32, enc_host, ne * 4, cudaMemcpyHostToDevice));
-    if (rc == WB_OK) rc = convert_f32_bf16(0, f32, enc, ne);
+    if (rc == WB_OK) rc = convert_f32_h16(0, f32, enc, ne);
     if (rc == WB_OK) rc = cross_attention_absorbed(0, qp, enc, ctx, B, S, D, H);
     if (rc == WB_OK && getenv("WB_XA_DBG")) {  // timestamp dump of CTA 0 (development aid)
         unsigned long long *d = nullptr;
@@ -867,7 +868,7 @@ int wb_debug_cross_attention_absorbed(const float *qp_host, const float *enc_hos
         cudaFree(d);
     }
     if (rc == WB_OK) {
-        bf16_to_f32_kernel<<<(unsigned)((nq + 255) / 256), 256>>>(ctx, f32, nq);
+        h16_to_f32_kernel<<<(unsigned)((nq + 255) / 256), 256>>>(ctx, f32, nq);
         ok(cudaGetLastError());
         ok(cudaMemcpy(ctx_host, f32, nq * 4, cudaMemcpyDeviceToHost));
     }

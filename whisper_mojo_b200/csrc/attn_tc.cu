@@ -29,7 +29,7 @@
 
 namespace wb {
 
-int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+int make_tmap_h16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                    uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
 
 static constexpr int ATT_THREADS = 192;
@@ -49,7 +49,7 @@ struct AttCfg {
 struct AttnTcParams {
     CUtensorMap qkv_map;  // dims (3D, S, B), box (64, 128, 1): Q tiles
     CUtensorMap kv_map;   // same tensor, box (64, KB, 1): K / V tiles
-    __nv_bfloat16 *out;   // [B*S][D]
+    h16 *out;   // [B*S][D]
     int S, D, H, n_kblocks;
     unsigned long long *dbg;  // optional SM-clock timestamp dump (development aid): [2 CTAs][2 roles][16 blocks][8 events]
     int dbg_cta1;             // linear id of the second traced CTA (the first one is CTA 0)
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
     } else if (warp == 5) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, KB, 0, 0);  // Q (K-major) x K (K-major)
-            constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
+            constexpr uint32_t idesc_s = ptx::umma_idesc_h16(128, KB, 0, 0);  // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_o = ptx::umma_idesc_h16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
             const uint64_t q_desc = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
             auto issue_s = [&](int j) {
                 const int s = j & 1;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
                 const uint64_t k_desc = ptx::umma_desc_sw128(ptx::smem_u32(sK + s * KV_BYTES), 1, 64);
                 EA_STAMP(1, j, 0);
 #pragma unroll
-                for (int k = 0; k < 4; k++) ptx::mma_bf16_ss(tS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+                for (int k = 0; k < 4; k++) ptx::mma_h16_ss(tS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
                 ptx::mma_commit(&k_empty[s]);
                 ptx::mma_commit(s_full);
             };
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
                         ptx::umma_desc_sw128(ptx::smem_u32(sP + (k >> 2) * TILE_BYTES), 1, 64) + 2 * (k & 3);
                     // V (MN-major): 16 keys = two 8-row groups of 1024 B.
                     const uint64_t v_desc = ptx::umma_desc_sw128(ptx::smem_u32(sV + k * 2048), 1, 64);
-                    ptx::mma_bf16_ss(tO, p_desc, v_desc, idesc_o, (j | k) != 0);
+                    ptx::mma_h16_ss(tO, p_desc, v_desc, idesc_o, (j | k) != 0);
                 }
                 ptx::mma_commit(pv_done);
             }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
                 const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(v[t]), __uint_as_float(v[t + 1])), c2, nmc2);
                 const float2 p01 = make_float2(ptx::ex2(a0.x), ptx::ex2(a0.y));
                 l01 = __fadd2_rn(l01, p01);
-                v[t >> 1] = pack_bf16x2(p01.x, p01.y);
+                v[t >> 1] = pack_h2(p01.x, p01.y);
             }
             l_run = l_run * alpha + (l01.x + l01.y);
             if (threadIdx.x == 0) EA_STAMP(0, j, 3);
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
         ptx::tc_fence_after();
         const float inv = 1.0f / l_run;
         const int q = q0 + row;
-        __nv_bfloat16 *dst = P.out + ((size_t)b * P.S + q) * P.D + h * 64;
+        h16 *dst = P.out + ((size_t)b * P.S + q) * P.D + h * 64;
 #pragma unroll 1
         for (int cc = 0; cc < 2; cc++) {
             uint32_t o[32];
@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
 #pragma unroll
                 for (int t = 0; t < 32; t += 8) {
                     uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(o[t]) * inv, __uint_as_float(o[t + 1]) * inv);
-                    u.y = pack_bf16x2(__uint_as_float(o[t + 2]) * inv, __uint_as_float(o[t + 3]) * inv);
-                    u.z = pack_bf16x2(__uint_as_float(o[t + 4]) * inv, __uint_as_float(o[t + 5]) * inv);
-                    u.w = pack_bf16x2(__uint_as_float(o[t + 6]) * inv, __uint_as_float(o[t + 7]) * inv);
+                    u.x = pack_h2(__uint_as_float(o[t]) * inv, __uint_as_float(o[t + 1]) * inv);
+                    u.y = pack_h2(__uint_as_float(o[t + 2]) * inv, __uint_as_float(o[t + 3]) * inv);
+                    u.z = pack_h2(__uint_as_float(o[t + 4]) * inv, __uint_as_float(o[t + 5]) * inv);
+                    u.w = pack_h2(__uint_as_float(o[t + 6]) * inv, __uint_as_float(o[t + 7]) * inv);
                     *reinterpret_cast<uint4 *>(dst + cc * 32 + t) = u;
                 }
             }
@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(ATT_THREADS, AttCfg<KB>::MIN_CTAS)
 }
 
 template <int KB, bool DBG>
-static int launch_attn(cudaStream_t st, AttnTcParams &P, const __nv_bfloat16 *qkv, int B, int S, int H, int D) {
-    WB_CHECK(make_tmap_bf16(&P.kv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D, (uint64_t)S * 3 * D,
+static int launch_attn(cudaStream_t st, AttnTcParams &P, const h16 *qkv, int B, int S, int H, int D) {
+    WB_CHECK(make_tmap_h16(&P.kv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D, (uint64_t)S * 3 * D,
                             KB, 3));
     P.n_kblocks = cdiv(S, KB);
     static bool opted = false;
@@ -307,11 +307,11 @@ unsigned long long *g_ea_dbg = nullptr;  // set by the debug hook (WB_EA_DBG) to
 int g_ea_dbg_cta1 = 148;
 int g_attn_kb = 128;  // keys per block of the encoder attention kernel (WB_ATTN_KB=64: 3-CTA/SM variant, measured equal)
 
-int encoder_attention_tc(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D) {
+int encoder_attention_tc(cudaStream_t st, const h16 *qkv, h16 *out, int B, int S, int H, int D) {
     if (B <= 0) return WB_OK;
     WB_ARG(D == H * 64, "encoder_attention_tc: head_dim must be 64");
     AttnTcParams P;
-    WB_CHECK(make_tmap_bf16(&P.qkv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D,
+    WB_CHECK(make_tmap_h16(&P.qkv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D,
                             (uint64_t)S * 3 * D, 128, 3));
     P.out = out, P.S = S, P.D = D, P.H = H;
     P.dbg = g_ea_dbg, P.dbg_cta1 = g_ea_dbg_cta1;

@@ -1,6 +1,6 @@
 // common.cuh -- shared helpers for the sm_100a kernels of libwhisper_b200.
 #pragma once
-#include <cuda_bf16.h>
+#include "dtype.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -93,17 +93,17 @@ __device__ __forceinline__ float gelu_ref(float x) {
     return 0.5f * x * (1.0f + tanhf(inner));
 }
 
-__device__ __forceinline__ void bf16x8_to_float(const uint4 &v, float *f) {
-    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+__device__ __forceinline__ void h8_to_float(const uint4 &v, float *f) {
+    const h16x2 *p = reinterpret_cast<const h16x2 *>(&v);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        float2 t = __bfloat1622float2(p[i]);
+        float2 t = h22f2(p[i]);
         f[2 * i] = t.x;
         f[2 * i + 1] = t.y;
     }
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    h16x2 t = f22h2(a, b);
     return *reinterpret_cast<uint32_t *>(&t);
 }
 

@@ -36,7 +36,7 @@
 
 namespace wb {
 
-int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+int make_tmap_h16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                    uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
 
 static constexpr int XA_THREADS = 224;
@@ -49,7 +49,7 @@ static constexpr int xa_keys(int atoms) { return atoms <= 6 ? 128 : 64; }
 struct CrossAttnParams {
     CUtensorMap enc_map;  // dims (D, S, B), box (64, KEYS, 1)
     CUtensorMap q_map;    // dims (D, H, B), box (64, 16, 1): rows >= H are zero filled
-    __nv_bfloat16 *ctx;   // [B][H*D]
+    h16 *ctx;   // [B][H*D]
     int B, S, D, H, n_blocks, atoms;
     unsigned long long *dbg;  // optional timestamp dump (CTA 0): [role][block][event]
 };
@@ -215,7 +215,7 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
     } else if (warp == 5) {
         // ===== MMA issuer 1: scores =====
         if (lane == 0) {
-            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(KEYS, 16, 0, 0);  // enc (K-major) x Q' (K-major)
+            constexpr uint32_t idesc_s = ptx::umma_idesc_h16(KEYS, 16, 0, 0);  // enc (K-major) x Q' (K-major)
             uint64_t a_desc0[2], b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
             for (int s = 0; s < 2; s++) a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), 1, 64);
             int g = 0, ci = 0;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
                         const int part = a >> 1;
 #pragma unroll
                         for (int k = 0; k < 4; k++)  // 4 K-steps of 16 channels; descriptors advance in 16-byte units
-                            ptx::mma_bf16_ss(tS0 + 16 * (s * n_acc + part), a_desc0[s] + a * (ATOM_BYTES >> 4) + 2 * k,
+                            ptx::mma_h16_ss(tS0 + 16 * (s * n_acc + part), a_desc0[s] + a * (ATOM_BYTES >> 4) + 2 * k,
                                              b_desc0 + a * (QATOM_BYTES >> 4) + 2 * k, idesc_s, ((a & 1) | k) != 0);
                     }
                     ptx::mma_commit(&s_full[s]);
@@ -244,7 +244,7 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
     } else if (warp == 6) {
         // ===== MMA issuer 2: context =====
         if (lane == 0) {
-            constexpr uint32_t idesc_c = ptx::umma_idesc_bf16(128, 16, 1, 0);  // enc^T (MN-major) x P^T (K-major)
+            constexpr uint32_t idesc_c = ptx::umma_idesc_h16(128, 16, 1, 0);  // enc^T (MN-major) x P^T (K-major)
             uint64_t a_desc0[2];
             // A = enc_blk^T: channels [128 m, 128 m + 128) = atoms 2m, 2m+1 (LBO = one atom),
             // K = keys: 8-row groups 1024 B apart, 16 keys per MMA = 2048 B
@@ -264,7 +264,7 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
                     for (int m = 0; m < n_acc; m++) {  // atom pair m = channels [128 m, 128 m + 128)
 #pragma unroll
                         for (int k = 0; k < KEYS / 16; k++)
-                            ptx::mma_bf16_ss(tC + 16 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
+                            ptx::mma_h16_ss(tC + 16 * m, a_desc0[s] + (2 * m) * (ATOM_BYTES >> 4) + k * (2048 >> 4),
                                              p_desc0 + (g & 1) * (P_BYTES >> 4) + (k >> 2) * (QATOM_BYTES >> 4) + 2 * (k & 3),
                                              idesc_c, (j | k) != 0);
                         ptx::mma_commit(&enc_empty[s * (XA_MAX_ATOMS / 2) + m]);
@@ -303,14 +303,14 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
 #pragma unroll
             for (int h = 0; h < H; h++) inv[h] = 1.0f / (s_red[h] + s_red[16 + h] + s_red[32 + h] + s_red[48 + h]);
             ptx::tc_fence_after();
-            __nv_bfloat16 *dst = P.ctx + (size_t)b_out * H * D;
+            h16 *dst = P.ctx + (size_t)b_out * H * D;
             for (int m = 0; m < n_acc; m++) {
                 uint32_t cv[16];
                 tmem_ld_32x32b_x16(tC + 16 * m + lane_addr, cv);
                 ptx::tmem_ld_wait();
                 const int c = ch0 + m * 128 + row;
 #pragma unroll
-                for (int h = 0; h < H; h++) dst[(size_t)h * D + c] = __float2bfloat16(__uint_as_float(cv[h]) * inv[h]);
+                for (int h = 0; h < H; h++) dst[(size_t)h * D + c] = f2h(__uint_as_float(cv[h]) * inv[h]);
             }
             ptx::tc_fence_before();
             named_bar_sync(2, 128);  // s_red reads are done; C buffer drained by all four warps
@@ -410,8 +410,8 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
                         float p = valid ? exp2f(sc[h] - m_run[h]) : 0.f;
                         l_part[h] = l_part[h] * alpha[h] + p;
                         if (owns_key)
-                            *reinterpret_cast<__nv_bfloat16 *>(atom + h * 128 + (((kk >> 3) ^ (h & 7)) << 4) + (kk & 7) * 2) =
-                                __float2bfloat16(p);
+                            *reinterpret_cast<h16 *>(atom + h * 128 + (((kk >> 3) ^ (h & 7)) << 4) + (kk & 7) * 2) =
+                                f2h(p);
                     }
                 }
                 // rescale the running context when a head's maximum moved (uniform across the CTA)
@@ -487,7 +487,7 @@ bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 7
 // -> ctx bf16 [B][H*D] with ctx[b][h] = softmax_j(q'_h . enc_j) weighted sum of enc_j.
 unsigned long long *g_xa_dbg = nullptr;  // set by the debug hook to collect timestamps
 
-int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __nv_bfloat16 *enc, __nv_bfloat16 *ctx,
+int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16 *ctx,
                              int B, int S, int D, int H) {
     if (B <= 0) return WB_OK;
     WB_ARG(cross_attn_absorbed_supported(D, H) && H * 64 == D,
@@ -495,8 +495,8 @@ int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __n
     CrossAttnParams P;
     const bool pair = xa_use_pair(D / 64);
     const int keys = xa_keys(pair ? D / 128 : D / 64);
-    WB_CHECK(make_tmap_bf16(&P.enc_map, enc, (uint64_t)D, (uint64_t)S, (uint64_t)B, (uint64_t)D, (uint64_t)S * D, keys, 3));
-    WB_CHECK(make_tmap_bf16(&P.q_map, qp, (uint64_t)D, (uint64_t)H, (uint64_t)B, (uint64_t)D, (uint64_t)H * D, 16, 3));
+    WB_CHECK(make_tmap_h16(&P.enc_map, enc, (uint64_t)D, (uint64_t)S, (uint64_t)B, (uint64_t)D, (uint64_t)S * D, keys, 3));
+    WB_CHECK(make_tmap_h16(&P.q_map, qp, (uint64_t)D, (uint64_t)H, (uint64_t)B, (uint64_t)D, (uint64_t)H * D, 16, 3));
     P.ctx = ctx, P.B = B, P.S = S, P.D = D, P.H = H, P.n_blocks = cdiv(S, keys), P.atoms = D / 64;
     P.dbg = g_xa_dbg;
     const size_t smem = cross_attn_absorbed_smem(D);

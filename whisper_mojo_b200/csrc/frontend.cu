@@ -174,7 +174,7 @@ __global__ void logmel_finalize_kernel(float *__restrict__ mel, const int *__res
 }
 
 // [n_mels][n_frames] f32 -> [n_frames][128] bf16 through a 32x33 shared tile.
-__global__ void mel_to_bf16_T_kernel(const float *__restrict__ mel, __nv_bfloat16 *__restrict__ out, int n_mels,
+__global__ void mel_to_h16_T_kernel(const float *__restrict__ mel, h16 *__restrict__ out, int n_mels,
                                      int n_frames) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, f0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
@@ -186,7 +186,7 @@ __global__ void mel_to_bf16_T_kernel(const float *__restrict__ mel, __nv_bfloat1
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
         int f = f0 + i, m = m0 + threadIdx.x;
-        if (f < n_frames) out[((size_t)b * n_frames + f) * 128 + m] = __float2bfloat16(tile[threadIdx.x][i]);
+        if (f < n_frames) out[((size_t)b * n_frames + f) * 128 + m] = f2h(tile[threadIdx.x][i]);
     }
 }
 
@@ -307,10 +307,10 @@ int logmel_finalize(cudaStream_t st, float *mel, const int *chunk_max_enc, int B
     return WB_OK;
 }
 
-int mel_to_bf16_T(cudaStream_t st, const float *mel, __nv_bfloat16 *out, int B, int n_mels, int n_frames) {
+int mel_to_h16_T(cudaStream_t st, const float *mel, h16 *out, int B, int n_mels, int n_frames) {
     if (B <= 0) return WB_OK;
     dim3 grid(cdiv(n_frames, 32), 4, B), block(32, 8);  // 4 x 32 = 128 channels (>= n_mels zero)
-    mel_to_bf16_T_kernel<<<grid, block, 0, st>>>(mel, out, n_mels, n_frames);
+    mel_to_h16_T_kernel<<<grid, block, 0, st>>>(mel, out, n_mels, n_frames);
     WB_LAUNCHED();
     return WB_OK;
 }

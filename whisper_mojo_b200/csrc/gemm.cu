@@ -47,10 +47,10 @@ struct GemmDev {
     int *part_idx;
     float *logits;
     // reference-kernel operand addressing
-    const __nv_bfloat16 *A;
+    const h16 *A;
     long long a_batch_stride;
     int lda, src_rows, conv_stride, pad, Cin;
-    const __nv_bfloat16 *W;
+    const h16 *W;
 };
 
 struct GemmTcParams {
@@ -107,8 +107,8 @@ __device__ __forceinline__ void epilogue_scalar(const GemmDev &p, int b, int m, 
     long long off;
     out_location(p, grow, n, seg, off);
     switch (p.epi) {
-        case EPI_STORE_BF16: reinterpret_cast<__nv_bfloat16 *>(p.out[seg])[off] = __float2bfloat16(v); break;
-        case EPI_GELU_BF16: reinterpret_cast<__nv_bfloat16 *>(p.out[seg])[off] = __float2bfloat16(gelu_ref(v)); break;
+        case EPI_STORE_H16: reinterpret_cast<h16 *>(p.out[seg])[off] = f2h(v); break;
+        case EPI_GELU_H16: reinterpret_cast<h16 *>(p.out[seg])[off] = f2h(gelu_ref(v)); break;
         case EPI_RESID_F32: reinterpret_cast<float *>(p.out[seg])[off] += v; break;
         case EPI_STORE_F32: reinterpret_cast<float *>(p.out[seg])[off] = v; break;
         case EPI_GELU_POS_F32:
@@ -135,10 +135,10 @@ __global__ void __launch_bounds__(256) gemm_ref_kernel(const GemmDev p) {
             int srow = m * p.conv_stride + tap - p.pad;
             float av = 0.f;
             if (m < p.rows_per_batch && kk < p.K && srow >= 0 && srow < p.src_rows)
-                av = __bfloat162float(p.A[(long long)b * p.a_batch_stride + (long long)srow * p.lda + ci]);
+                av = h2f(p.A[(long long)b * p.a_batch_stride + (long long)srow * p.lda + ci]);
             As[c][r] = av;
             int n = n0 + r;
-            Bs[c][r] = (n < p.N && kk < p.K) ? __bfloat162float(p.W[(long long)n * p.K + kk]) : 0.f;
+            Bs[c][r] = (n < p.N && kk < p.K) ? h2f(p.W[(long long)n * p.K + kk]) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -201,8 +201,8 @@ __device__ __forceinline__ void epi_prefetch(const GemmDev &p, int b, int m, int
     int seg;
     long long off;
     out_location(p, grow, n, seg, off);
-    if (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16) {
-        e.dst = reinterpret_cast<__nv_bfloat16 *>(p.out[seg]) + off;
+    if (EPI == EPI_STORE_H16 || EPI == EPI_GELU_H16) {
+        e.dst = reinterpret_cast<h16 *>(p.out[seg]) + off;
         e.vec = e.full && ((reinterpret_cast<uintptr_t>(e.dst) & 15) == 0);
         return;
     }
@@ -259,29 +259,29 @@ __device__ __forceinline__ void epi_finish(const GemmDev &p, int b, int m, int n
         }
         return;
     }
-    if (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16) {
-        if (EPI == EPI_GELU_BF16) {
+    if (EPI == EPI_STORE_H16 || EPI == EPI_GELU_H16) {
+        if (EPI == EPI_GELU_H16) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 const float2 g = gelu_fast2(make_float2(v[j], v[j + 1]));
                 v[j] = g.x, v[j + 1] = g.y;
             }
         }
-        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(e.dst);
+        h16 *dst = reinterpret_cast<h16 *>(e.dst);
         if (e.vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 uint4 u;
-                u.x = pack_bf16x2(v[j], v[j + 1]);
-                u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                u.x = pack_h2(v[j], v[j + 1]);
+                u.y = pack_h2(v[j + 2], v[j + 3]);
+                u.z = pack_h2(v[j + 4], v[j + 5]);
+                u.w = pack_h2(v[j + 6], v[j + 7]);
                 *reinterpret_cast<uint4 *>(dst + j) = u;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j++)
-                if (n + j < p.N) dst[j] = __float2bfloat16(v[j]);
+                if (n + j < p.N) dst[j] = f2h(v[j]);
         }
         return;
     }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, 0, 0);
+            constexpr uint32_t idesc = ptx::umma_idesc_h16(BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES), 1, 64);
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)  // +32 bytes (2 x 16 B units) per UMMA_K step inside the atom
-                        ptx::mma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        ptx::mma_h16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     ptx::mma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) stage = 0, phase ^= 1;
                 }
@@ -536,7 +536,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, BN2, 0, 0);
+            constexpr uint32_t idesc = ptx::umma_idesc_h16(256, BN2, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -554,7 +554,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                     const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sb), 1, 64);
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)
-                        ptx::mma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        ptx::mma_h16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     ptx::mma_commit_pair(&empty_bar[stage], 3);
                     if (++stage == PAIR_STAGES) stage = 0, phase ^= 1;
                 }
@@ -619,7 +619,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                             *reinterpret_cast<float4 *>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                                 make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     } else {
-                        if (EPI == EPI_GELU_BF16) {
+                        if (EPI == EPI_GELU_H16) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 const float2 g = gelu_fast2(make_float2(o[j], o[j + 1]));
@@ -629,8 +629,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             *reinterpret_cast<uint4 *>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
-                                           pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+                                make_uint4(pack_h2(o[8 * j], o[8 * j + 1]), pack_h2(o[8 * j + 2], o[8 * j + 3]),
+                                           pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7]));
                     }
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
@@ -685,7 +685,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 tensor map with a {64, box_rows, 1} box and 128-byte swizzle over a [d2][d1][d0] view.
-int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+int make_tmap_h16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                    uint64_t stride2_elems, uint32_t box_rows, int rank) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
@@ -696,7 +696,7 @@ int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
     cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
     cuuint32_t box[3] = {64, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims, strides,
+    CUresult r = fn(map, H16_TMAP_DTYPE, (cuuint32_t)rank, const_cast<void *>(base), dims, strides,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -854,7 +854,7 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
         p.a_row_off[t] = q;
         uint64_t nrows = d.src_rows > par ? (uint64_t)(d.src_rows - par + d.conv_stride - 1) / d.conv_stride : 0;
         WB_ARG(nrows > 0, "gemm(tc): empty tap view");
-        WB_CHECK(make_tmap_bf16(&P.a_map[t], d.A + (size_t)par * d.lda, (uint64_t)d.Cin, nrows, (uint64_t)d.batches,
+        WB_CHECK(make_tmap_h16(&P.a_map[t], d.A + (size_t)par * d.lda, (uint64_t)d.Cin, nrows, (uint64_t)d.batches,
                                 (uint64_t)d.conv_stride * d.lda,
                                 d.batches > 1 ? (uint64_t)d.a_batch_stride : (uint64_t)d.conv_stride * d.lda * nrows, BM,
                                 3));
@@ -883,15 +883,15 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
         // output routing is per 32-column chunk, so any tile width works; the argmax partials need 64-column pairs
         const int bn2 = d.epi == EPI_ARGMAX ? 256 : pick_pair_bn(d.N);
         for (int t = 0; t < 3; t++) Q.a_map[t] = P.a_map[t];
-        WB_CHECK(make_tmap_bf16(&Q.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, bn2 / 2, 2));
+        WB_CHECK(make_tmap_h16(&Q.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, bn2 / 2, 2));
         Q.d = p;
         Q.pair_tiles_m_per_batch = pair_tiles_m;
         Q.pair_tiles_n = cdiv(d.N, bn2);
         const int total = p.batches * pair_tiles_m * Q.pair_tiles_n;
         const int grid = 2 * std::min(total, sms / 2);
         switch (d.epi) {
-            case EPI_STORE_BF16:
-            case EPI_GELU_BF16:
+            case EPI_STORE_H16:
+            case EPI_GELU_H16:
             case EPI_RESID_F32:
             case EPI_STORE_F32: {
                 // plain [rows][N] output -> coalesced TMA stores / residual add by TMA reduce (fp32: the SM never
@@ -903,15 +903,15 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
                     const uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.rows_per_batch, (uint64_t)p.batches};
                     const uint64_t str[2] = {(uint64_t)d.out_ld[0] * esz, (uint64_t)d.rows_per_batch * d.out_ld[0] * esz};
                     const uint32_t box[3] = {32, 32, 1};
-                    WB_CHECK(make_tmap_any(&Q.out_map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    WB_CHECK(make_tmap_any(&Q.out_map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : H16_TMAP_DTYPE,
                                            esz == 4 ? 128 : 64, d.out[0], 3, dims, str, box));
-                    if (d.epi == EPI_STORE_BF16) return launch_pair_bn<EPI_STORE_BF16, true>(st, Q, grid, bn2);
-                    if (d.epi == EPI_GELU_BF16) return launch_pair_bn<EPI_GELU_BF16, true>(st, Q, grid, bn2);
+                    if (d.epi == EPI_STORE_H16) return launch_pair_bn<EPI_STORE_H16, true>(st, Q, grid, bn2);
+                    if (d.epi == EPI_GELU_H16) return launch_pair_bn<EPI_GELU_H16, true>(st, Q, grid, bn2);
                     if (d.epi == EPI_STORE_F32) return launch_pair_bn<EPI_STORE_F32, true>(st, Q, grid, bn2);
                     return launch_pair_bn<EPI_RESID_F32, true>(st, Q, grid, bn2);
                 }
-                if (d.epi == EPI_STORE_BF16) return launch_pair_bn<EPI_STORE_BF16>(st, Q, grid, bn2);
-                if (d.epi == EPI_GELU_BF16) return launch_pair_bn<EPI_GELU_BF16>(st, Q, grid, bn2);
+                if (d.epi == EPI_STORE_H16) return launch_pair_bn<EPI_STORE_H16>(st, Q, grid, bn2);
+                if (d.epi == EPI_GELU_H16) return launch_pair_bn<EPI_GELU_H16>(st, Q, grid, bn2);
                 if (d.epi == EPI_STORE_F32) return launch_pair_bn<EPI_STORE_F32>(st, Q, grid, bn2);
                 return launch_pair_bn<EPI_RESID_F32>(st, Q, grid, bn2);
             }
@@ -919,13 +919,13 @@ int gemm_run(cudaStream_t st, const GemmDesc &d, int impl) {
             case EPI_GELU_POS_F32: return launch_pair_bn<EPI_GELU_POS_F32>(st, Q, grid, bn2);
         }
     }
-    WB_CHECK(make_tmap_bf16(&P.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, BN, 2));
+    WB_CHECK(make_tmap_h16(&P.b_map, d.W, (uint64_t)p.K, (uint64_t)d.N, 1, (uint64_t)p.K, 0, BN, 2));
 
     int total_tiles = p.batches * p.tiles_m_per_batch * p.tiles_n;
     int grid = total_tiles < sms ? total_tiles : sms;
     switch (d.epi) {
-        case EPI_STORE_BF16: return launch_tc<EPI_STORE_BF16>(st, P, grid);
-        case EPI_GELU_BF16: return launch_tc<EPI_GELU_BF16>(st, P, grid);
+        case EPI_STORE_H16: return launch_tc<EPI_STORE_H16>(st, P, grid);
+        case EPI_GELU_H16: return launch_tc<EPI_GELU_H16>(st, P, grid);
         case EPI_RESID_F32: return launch_tc<EPI_RESID_F32>(st, P, grid);
         case EPI_STORE_F32: return launch_tc<EPI_STORE_F32>(st, P, grid);
         case EPI_ARGMAX: return launch_tc<EPI_ARGMAX>(st, P, grid);

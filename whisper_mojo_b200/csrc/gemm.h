@@ -6,15 +6,15 @@
 // projection (layers.mojo:148-157) and the tied-embedding logit projection fused with argmax
 // (whisper.mojo:159-166 + whisper_tensor.mojo:431-439).
 #pragma once
-#include <cuda_bf16.h>
+#include "dtype.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace wb {
 
 enum GemmEpi {
-    EPI_STORE_BF16 = 0,    // out_bf16 = acc + bias
-    EPI_GELU_BF16 = 1,     // out_bf16 = gelu(acc + bias)
+    EPI_STORE_H16 = 0,    // out_h16 = acc + bias
+    EPI_GELU_H16 = 1,     // out_h16 = gelu(acc + bias)
     EPI_RESID_F32 = 2,     // out_f32 += acc + bias               (residual add in place)
     EPI_STORE_F32 = 3,     // out_f32 = acc + bias
     EPI_ARGMAX = 4,        // per-row (max, first index) over each 128-column tile -> partials; optional f32 logits
@@ -30,14 +30,14 @@ enum GemmImpl { GEMM_IMPL_REF = 0, GEMM_IMPL_TC = 1, GEMM_IMPL_TC_SINGLE = 2, GE
 //   (zero when the source row is outside [0, src_rows)); plain GEMM: taps=1, conv_stride=1, pad=0.
 //   Output row index = b*rows_per_batch + m.
 struct GemmDesc {
-    const __nv_bfloat16 *A = nullptr;
+    const h16 *A = nullptr;
     int64_t a_batch_stride = 0;
     int lda = 0, src_rows = 0, conv_stride = 1, pad = 0, taps = 1, Cin = 0;
     int batches = 1, rows_per_batch = 0;
-    const __nv_bfloat16 *W = nullptr;  // [N][taps*Cin]
+    const h16 *W = nullptr;  // [N][taps*Cin]
     int N = 0;
     const float *bias = nullptr;
-    int epi = EPI_STORE_BF16;
+    int epi = EPI_STORE_H16;
     // Output routing.  Columns are split in segments of seg_cols (a multiple of 128, or N).
     // n_seg_ptrs > 0: segment s writes to out[s] with row stride out_ld[s] (+ dyn offset).
     // n_seg_ptrs == 0: segment s writes to out[0] + s*seg_stride with row stride out_ld[0].

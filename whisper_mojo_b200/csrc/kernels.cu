@@ -19,9 +19,9 @@ enum { LN_PLAIN = 0, LN_EMBED = 1, LN_RESID = 2 };
 // MODE LN_RESID: x[row] += bias + sum_s part[s][row] (fixed order: deterministic) before the LayerNorm -- the second
 // half of a split-K residual GEMM fused with the LayerNorm that follows it; gamma == nullptr skips the LN output.
 template <int EMBED>
-__global__ void __launch_bounds__(256) ln_bf16_kernel(const float *__restrict__ x_in, const float *__restrict__ gamma,
+__global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x_in, const float *__restrict__ gamma,
                                                       const float *__restrict__ beta, int rows, int D,
-                                                      __nv_bfloat16 *__restrict__ out_bf16,
+                                                      h16 *__restrict__ out_h16,
                                                       float *__restrict__ out_f32,
                                                       // EMBED only:
                                                       const float *__restrict__ tok_emb,
@@ -100,29 +100,29 @@ __global__ void __launch_bounds__(256) ln_bf16_kernel(const float *__restrict__ 
             r.z = (v[i].z - mean) * inv_std * g.z + b.z;
             r.w = (v[i].w - mean) * inv_std * g.w + b.w;
             uint2 pk;
-            pk.x = pack_bf16x2(r.x, r.y);
-            pk.y = pack_bf16x2(r.z, r.w);
-            reinterpret_cast<uint2 *>(out_bf16 + (size_t)row * D)[i * 32 + lane] = pk;
+            pk.x = pack_h2(r.x, r.y);
+            pk.y = pack_h2(r.z, r.w);
+            reinterpret_cast<uint2 *>(out_h16 + (size_t)row * D)[i * 32 + lane] = pk;
             if (out_f32) reinterpret_cast<float4 *>(out_f32 + (size_t)row * D)[i * 32 + lane] = r;
         }
 }
 
-int ln_bf16(cudaStream_t st, const float *x, const float *gamma, const float *beta, int rows, int D,
-            __nv_bfloat16 *out_bf16, float *out_f32) {
-    WB_ARG(D % 128 == 0 && D <= 1024, "ln_bf16: D=%d must be a multiple of 128 and <= 1024", D);
+int ln_h16(cudaStream_t st, const float *x, const float *gamma, const float *beta, int rows, int D,
+            h16 *out_h16, float *out_f32) {
+    WB_ARG(D % 128 == 0 && D <= 1024, "ln_h16: D=%d must be a multiple of 128 and <= 1024", D);
     if (rows <= 0) return WB_OK;
-    WB_CUDA(launch_pdl(ln_bf16_kernel<LN_PLAIN>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, gamma, beta, rows, D, out_bf16,
+    WB_CUDA(launch_pdl(ln_h16_kernel<LN_PLAIN>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, gamma, beta, rows, D, out_h16,
                        out_f32, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, 0, nullptr));
     WB_LAUNCHED();
     return WB_OK;
 }
 
 int resid_ln(cudaStream_t st, float *x, const float *part, int n_split, const float *bias, const float *gamma,
-             const float *beta, int rows, int D, __nv_bfloat16 *out_bf16) {
+             const float *beta, int rows, int D, h16 *out_h16) {
     WB_ARG(D % 128 == 0 && D <= 1024, "resid_ln: D=%d must be a multiple of 128 and <= 1024", D);
-    WB_ARG(x && part && n_split >= 1 && (!gamma || (beta && out_bf16)), "resid_ln: bad arguments");
+    WB_ARG(x && part && n_split >= 1 && (!gamma || (beta && out_h16)), "resid_ln: bad arguments");
     if (rows <= 0) return WB_OK;
-    WB_CUDA(launch_pdl(ln_bf16_kernel<LN_RESID>, dim3(cdiv(rows, 8)), dim3(256), 0, st, nullptr, gamma, beta, rows, D, out_bf16,
+    WB_CUDA(launch_pdl(ln_h16_kernel<LN_RESID>, dim3(cdiv(rows, 8)), dim3(256), 0, st, nullptr, gamma, beta, rows, D, out_h16,
                        nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, x, part, n_split, (long long)rows * D, bias));
     WB_LAUNCHED();
     return WB_OK;
@@ -130,10 +130,10 @@ int resid_ln(cudaStream_t st, float *x, const float *part, int n_split, const fl
 
 int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const int *cur_tok, const int *pos_dev,
              int B, int D, int vocab, int n_pos, const float *gamma, const float *beta, float *x,
-             __nv_bfloat16 *xn) {
+             h16 *xn) {
     WB_ARG(D % 128 == 0 && D <= 1024, "embed_ln: D=%d must be a multiple of 128 and <= 1024", D);
     if (B <= 0) return WB_OK;
-    WB_CUDA(launch_pdl(ln_bf16_kernel<LN_EMBED>, dim3(cdiv(B, 8)), dim3(256), 0, st, nullptr, gamma, beta, B, D, xn, nullptr,
+    WB_CUDA(launch_pdl(ln_h16_kernel<LN_EMBED>, dim3(cdiv(B, 8)), dim3(256), 0, st, nullptr, gamma, beta, B, D, xn, nullptr,
                        tok_emb, pos_emb, cur_tok, pos_dev, vocab, n_pos, x, nullptr, 0, 0, nullptr));
     WB_LAUNCHED();
     return WB_OK;
@@ -146,8 +146,8 @@ int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const 
 // Three phases as in the reference (scores -> softmax -> weighted sum); scores live in shared memory.
 // ---------------------------------------------------------------------------------------------
 struct DecodeAttnDev {
-    const __nv_bfloat16 *q, *K, *V;
-    __nv_bfloat16 *out;
+    const h16 *q, *K, *V;
+    h16 *out;
     long long kv_batch_stride;
     int H, D, len_const, len_add, splits, smem_len;
     const int *len_dev;
@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
     float *sc = s_scores + (size_t)h * p.smem_len;
 
     float qf[8];
-    bf16x8_to_float(*reinterpret_cast<const uint4 *>(p.q + (size_t)b * p.D + h * 64 + c * 8), qf);
+    h8_to_float(*reinterpret_cast<const uint4 *>(p.q + (size_t)b * p.D + h * 64 + c * 8), qf);
     const float scale = 0.125f;  // 1/sqrt(head_dim), head_dim = 64 (layers.mojo:184)
-    const __nv_bfloat16 *Kb = p.K + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
-    const __nv_bfloat16 *Vb = p.V + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
+    const h16 *Kb = p.K + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
+    const h16 *Vb = p.V + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
 
     // phase 1: scores
     float m = -1e10f;  // layers.mojo:188
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             float kf[8];
-            bf16x8_to_float(kv[u], kf);
+            h8_to_float(kv[u], kf);
             float d = 0.f;
 #pragma unroll
             for (int t = 0; t < 8; t++) d += qf[t] * kf[t];
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
             int jj = i + 4 * u;
             float pj = (jj < n) ? sc[jj] : 0.f;
             float vf[8];
-            bf16x8_to_float(vv[u], vf);
+            h8_to_float(vv[u], vf);
 #pragma unroll
             for (int t = 0; t < 8; t++) acc[t] += pj * vf[t];
         }
@@ -252,10 +252,10 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
         if (sub == 0) {
             const float inv = 1.0f / l;
             uint4 o;
-            o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-            o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-            o.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
-            o.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+            o.x = pack_h2(acc[0] * inv, acc[1] * inv);
+            o.y = pack_h2(acc[2] * inv, acc[3] * inv);
+            o.z = pack_h2(acc[4] * inv, acc[5] * inv);
+            o.w = pack_h2(acc[6] * inv, acc[7] * inv);
             *reinterpret_cast<uint4 *>(p.out + (size_t)b * p.D + h * 64 + c * 8) = o;
         }
     } else {
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
 }
 
 // Merge split-K partials: one warp per (b, h); lane owns 2 head dims.
-__global__ void decode_attn_combine_kernel(const float *__restrict__ ws, __nv_bfloat16 *__restrict__ out, int B, int H,
+__global__ void decode_attn_combine_kernel(const float *__restrict__ ws, h16 *__restrict__ out, int B, int H,
                                            int D, int splits) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= B * H) return;
@@ -285,7 +285,7 @@ __global__ void decode_attn_combine_kernel(const float *__restrict__ ws, __nv_bf
         o1 += p[2 * lane + 1] * f;
     }
     float inv = 1.0f / l;
-    *reinterpret_cast<uint32_t *>(out + (size_t)b * D + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+    *reinterpret_cast<uint32_t *>(out + (size_t)b * D + h * 64 + 2 * lane) = pack_h2(o0 * inv, o1 * inv);
 }
 
 // Split-K factor for a constant key length.  Every CTA streams the same number of K/V bytes, so the
@@ -351,20 +351,20 @@ int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {
 // ---------------------------------------------------------------------------------------------
 // Encoder attention, bring-up version: one warp per query row, scores in shared memory.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) encoder_attn_ref_kernel(const __nv_bfloat16 *__restrict__ qkv,
-                                                               __nv_bfloat16 *__restrict__ out, int S, int H, int D) {
+__global__ void __launch_bounds__(256) encoder_attn_ref_kernel(const h16 *__restrict__ qkv,
+                                                               h16 *__restrict__ out, int S, int H, int D) {
     extern __shared__ float s_sc[];  // [8][S]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x * 8 + warp, h = blockIdx.y, b = blockIdx.z;
     if (qi >= S) return;
     float *sc = s_sc + (size_t)warp * S;
     const size_t ld = 3 * (size_t)D;
-    const __nv_bfloat16 *base = qkv + (size_t)b * S * ld;
-    float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(base + (size_t)qi * ld + h * 64 + 2 * lane));
+    const h16 *base = qkv + (size_t)b * S * ld;
+    float2 qv = h22f2(*reinterpret_cast<const h16x2 *>(base + (size_t)qi * ld + h * 64 + 2 * lane));
     float m = -INFINITY;
     for (int j = 0; j < S; j++) {
-        float2 kv = __bfloat1622float2(
-            *reinterpret_cast<const __nv_bfloat162 *>(base + (size_t)j * ld + D + h * 64 + 2 * lane));
+        float2 kv = h22f2(
+            *reinterpret_cast<const h16x2 *>(base + (size_t)j * ld + D + h * 64 + 2 * lane));
         float d = warp_sum(qv.x * kv.x + qv.y * kv.y) * 0.125f;
         m = fmaxf(m, d);
         if (lane == 0) sc[j] = d;
@@ -380,17 +380,17 @@ __global__ void __launch_bounds__(256) encoder_attn_ref_kernel(const __nv_bfloat
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
     for (int j = 0; j < S; j++) {
-        float2 vv = __bfloat1622float2(
-            *reinterpret_cast<const __nv_bfloat162 *>(base + (size_t)j * ld + 2 * D + h * 64 + 2 * lane));
+        float2 vv = h22f2(
+            *reinterpret_cast<const h16x2 *>(base + (size_t)j * ld + 2 * D + h * 64 + 2 * lane));
         float pj = sc[j];
         o0 += pj * vv.x;
         o1 += pj * vv.y;
     }
     float inv = 1.0f / l;
-    *reinterpret_cast<uint32_t *>(out + ((size_t)b * S + qi) * D + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+    *reinterpret_cast<uint32_t *>(out + ((size_t)b * S + qi) * D + h * 64 + 2 * lane) = pack_h2(o0 * inv, o1 * inv);
 }
 
-int encoder_attention_ref(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D) {
+int encoder_attention_ref(cudaStream_t st, const h16 *qkv, h16 *out, int B, int S, int H, int D) {
     if (B <= 0) return WB_OK;
     size_t smem = (size_t)8 * S * sizeof(float);
     static size_t smem_opted = 48 * 1024;
@@ -467,20 +467,20 @@ int greedy_advance(cudaStream_t st, const GreedyState &g, int B, int mode, int n
 // ---------------------------------------------------------------------------------------------
 // Weight conversion
 // ---------------------------------------------------------------------------------------------
-__global__ void convert_f32_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, size_t n) {
+__global__ void convert_f32_h16_kernel(const float *__restrict__ src, h16 *__restrict__ dst, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) dst[i] = __float2bfloat16(src[i]);
+    for (; i < n; i += stride) dst[i] = f2h(src[i]);
 }
-int convert_f32_bf16(cudaStream_t st, const float *src, __nv_bfloat16 *dst, size_t n) {
+int convert_f32_h16(cudaStream_t st, const float *src, h16 *dst, size_t n) {
     if (!n) return WB_OK;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    convert_f32_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+    convert_f32_h16_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
     WB_LAUNCHED();
     return WB_OK;
 }
 
-__global__ void convert_conv_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ dst, int C_out,
+__global__ void convert_conv_weight_kernel(const float *__restrict__ w, h16 *__restrict__ dst, int C_out,
                                            int C_in, int C_in_pad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = (size_t)C_out * 3 * C_in_pad;
@@ -489,9 +489,9 @@ __global__ void convert_conv_weight_kernel(const float *__restrict__ w, __nv_bfl
     int k = (int)((i / C_in_pad) % 3);
     int co = (int)(i / ((size_t)3 * C_in_pad));
     float v = ci < C_in ? w[((size_t)co * C_in + ci) * 3 + k] : 0.f;
-    dst[i] = __float2bfloat16(v);
+    dst[i] = f2h(v);
 }
-int convert_conv_weight(cudaStream_t st, const float *w, __nv_bfloat16 *dst, int C_out, int C_in, int C_in_pad) {
+int convert_conv_weight(cudaStream_t st, const float *w, h16 *dst, int C_out, int C_in, int C_in_pad) {
     size_t n = (size_t)C_out * 3 * C_in_pad;
     convert_conv_weight_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, dst, C_out, C_in, C_in_pad);
     WB_LAUNCHED();
@@ -502,7 +502,7 @@ int convert_conv_weight(cudaStream_t st, const float *w, __nv_bfloat16 *dst, int
 // Folding of the cross-attention projections (see kernels.h); one thread per output element.
 // ---------------------------------------------------------------------------------------------
 __global__ void fold_qk_kernel(const float *__restrict__ Wq, const float *__restrict__ bq,
-                               const float *__restrict__ Wk, int D, int H, __nv_bfloat16 *__restrict__ Wqk,
+                               const float *__restrict__ Wk, int D, int H, h16 *__restrict__ Wqk,
                                float *__restrict__ bqk) {
     const float alpha = 0.125f * 1.4426950408889634f;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,12 +516,12 @@ __global__ void fold_qk_kernel(const float *__restrict__ Wq, const float *__rest
         float wk = Wk[(size_t)(h * 64 + d) * D + c];
         acc += wk * (i < D ? Wq[(size_t)(h * 64 + d) * D + i] : bq[h * 64 + d]);
     }
-    if (i < D) Wqk[(size_t)hc * D + i] = __float2bfloat16(acc * alpha);
+    if (i < D) Wqk[(size_t)hc * D + i] = f2h(acc * alpha);
     else bqk[hc] = acc * alpha;
 }
 __global__ void fold_ov_kernel(const float *__restrict__ Wv, const float *__restrict__ bv,
                                const float *__restrict__ Wo, const float *__restrict__ bo, int D, int H,
-                               __nv_bfloat16 *__restrict__ Wov, float *__restrict__ bov) {
+                               h16 *__restrict__ Wov, float *__restrict__ bov) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = (size_t)D * (H * D + 1);
     if (idx >= n) return;
@@ -531,7 +531,7 @@ __global__ void fold_ov_kernel(const float *__restrict__ Wv, const float *__rest
         int h = col / D, c = col % D;
         float acc = 0.f;
         for (int d = 0; d < 64; d++) acc += Wo[(size_t)row * D + h * 64 + d] * Wv[(size_t)(h * 64 + d) * D + c];
-        Wov[(size_t)row * H * D + col] = __float2bfloat16(acc);
+        Wov[(size_t)row * H * D + col] = f2h(acc);
     } else {
         float acc = bo[row];
         for (int j = 0; j < D; j++) acc += Wo[(size_t)row * D + j] * bv[j];
@@ -539,8 +539,8 @@ __global__ void fold_ov_kernel(const float *__restrict__ Wv, const float *__rest
     }
 }
 int fold_cross_weights(cudaStream_t st, const float *Wq, const float *bq, const float *Wk, const float *Wv,
-                       const float *bv, const float *Wo, const float *bo, int D, int H, __nv_bfloat16 *Wqk,
-                       float *bqk, __nv_bfloat16 *Wov, float *bov) {
+                       const float *bv, const float *Wo, const float *bo, int D, int H, h16 *Wqk,
+                       float *bqk, h16 *Wov, float *bov) {
     size_t n1 = (size_t)H * D * (D + 1), n2 = (size_t)D * ((size_t)H * D + 1);
     fold_qk_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(Wq, bq, Wk, D, H, Wqk, bqk);
     WB_LAUNCHED();

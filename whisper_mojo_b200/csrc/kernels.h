@@ -1,26 +1,26 @@
 // kernels.h -- launchers for the non-GEMM kernels of the batched fast path (kernels.cu, frontend.cu).
 #pragma once
-#include <cuda_bf16.h>
+#include "dtype.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace wb {
 
 // LayerNorm (whisper_tensor.mojo:249-285, one-pass variance) fp32 in -> bf16 out (+ optional fp32 out).
-int ln_bf16(cudaStream_t st, const float *x, const float *gamma, const float *beta, int rows, int D,
-            __nv_bfloat16 *out_bf16, float *out_f32);
+int ln_h16(cudaStream_t st, const float *x, const float *gamma, const float *beta, int rows, int D,
+            h16 *out_h16, float *out_f32);
 
 // Second half of a split-K residual GEMM fused with the LayerNorm that follows it (layers.mojo:456-461,486-491,
 // 515-517 + the next block's LayerNorm): x[row] += bias + part[0][row] + ... + part[n_split-1][row] in that
-// fixed order, then out_bf16[row] = LN(x[row]) unless gamma is null.  part is [n_split][rows][D] fp32.
+// fixed order, then out_h16[row] = LN(x[row]) unless gamma is null.  part is [n_split][rows][D] fp32.
 int resid_ln(cudaStream_t st, float *x, const float *part, int n_split, const float *bias, const float *gamma,
-             const float *beta, int rows, int D, __nv_bfloat16 *out_bf16);
+             const float *beta, int rows, int D, h16 *out_h16);
 
 // Decoder input (whisper.mojo:138-149) fused with the first LayerNorm of layer 0:
 //   x[b] = token_emb[cur_tok[b]] + pos_emb[*pos];  xn[b] = LN(x[b]) in bf16.
 int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const int *cur_tok, const int *pos_dev,
              int B, int D, int vocab, int n_pos, const float *gamma, const float *beta, float *x,
-             __nv_bfloat16 *xn);
+             h16 *xn);
 
 // Single-query attention for one decode step (layers.mojo:186-272), batched over chunks and heads.
 //   q   bf16 [B][D]                         (head h = columns h*64 .. h*64+63)
@@ -29,8 +29,8 @@ int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const 
 //   out bf16 [B][D]
 // `ws` is scratch for the split-K partials: floats [B][splits][H][66].
 struct DecodeAttnArgs {
-    const __nv_bfloat16 *q, *K, *V;
-    __nv_bfloat16 *out;
+    const h16 *q, *K, *V;
+    h16 *out;
     int64_t kv_batch_stride;
     int B, H, D;
     int len_const;
@@ -45,13 +45,13 @@ int decode_attention_splits(int B, int len, int H);
 
 // Encoder self-attention, bring-up implementation on CUDA cores (layers.mojo:273-342, no mask):
 // qkv bf16 [B*S][3D] -> out bf16 [B*S][D].
-int encoder_attention_ref(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D);
+int encoder_attention_ref(cudaStream_t st, const h16 *qkv, h16 *out, int B, int S, int H, int D);
 // Same contract on tcgen05 tensor cores, flash-attention style (attn_tc.cu).
-int encoder_attention_tc(cudaStream_t st, const __nv_bfloat16 *qkv, __nv_bfloat16 *out, int B, int S, int H, int D);
+int encoder_attention_tc(cudaStream_t st, const h16 *qkv, h16 *out, int B, int S, int H, int D);
 
 // Decode cross-attention over enc_out itself (cross_attn_tc.cu): q' bf16 [B][H*D], enc bf16 [B][S][D]
 // -> ctx bf16 [B][H*D].  Needs the folded weights below.
-int cross_attention_absorbed(cudaStream_t st, const __nv_bfloat16 *qp, const __nv_bfloat16 *enc, __nv_bfloat16 *ctx,
+int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16 *ctx,
                              int B, int S, int D, int H);
 bool cross_attn_absorbed_supported(int D, int H);
 extern unsigned long long *g_xa_dbg;  // development aid: timestamp buffer for CTA 0 (normally null)
@@ -59,8 +59,8 @@ extern unsigned long long *g_xa_dbg;  // development aid: timestamp buffer for C
 //   Wqk[h*D + c][i] = (log2(e)/8) * sum_d Wk[h*64+d][c] * Wq[h*64+d][i],  bqk[h*D + c] = (log2(e)/8) * sum_d Wk[h*64+d][c] * bq[h*64+d]
 //   Wov[n][h*D + c] = sum_d Wo[n][h*64+d] * Wv[h*64+d][c],                  bov[n] = bo[n] + sum_j Wo[n][j] * bv[j]
 int fold_cross_weights(cudaStream_t st, const float *Wq, const float *bq, const float *Wk, const float *Wv,
-                       const float *bv, const float *Wo, const float *bo, int D, int H, __nv_bfloat16 *Wqk,
-                       float *bqk, __nv_bfloat16 *Wov, float *bov);
+                       const float *bv, const float *Wo, const float *bo, int D, int H, h16 *Wqk,
+                       float *bqk, h16 *Wov, float *bov);
 
 // Greedy bookkeeping after a logits step (whisper.mojo:198-221): append next token unless the chunk
 // has finished, mark EOT, set the next input token, advance cur_len / pos.
@@ -101,12 +101,12 @@ int logmel_raw_tc(cudaStream_t st, FrontendTables &t, const float *pcm, int B, i
 // Finalise in place: v = (max(v, chunk_max - 8) + 4) / 4.
 int logmel_finalize(cudaStream_t st, float *mel, const int *chunk_max_enc, int B, int n_mels, int n_frames);
 // mel f32 [B][n_mels][n_frames] -> bf16 [B][n_frames][128] (channels >= n_mels zero) for the conv1 GEMM.
-int mel_to_bf16_T(cudaStream_t st, const float *mel, __nv_bfloat16 *out, int B, int n_mels, int n_frames);
+int mel_to_h16_T(cudaStream_t st, const float *mel, h16 *out, int B, int n_mels, int n_frames);
 
 // fp32 -> bf16 conversion helpers used at weight load.
-int convert_f32_bf16(cudaStream_t st, const float *src, __nv_bfloat16 *dst, size_t n);
+int convert_f32_h16(cudaStream_t st, const float *src, h16 *dst, size_t n);
 // conv weight [C_out][C_in][3] fp32 -> bf16 [C_out][3*C_in_pad] in the (tap, ci) order of
 // transpose_conv_weights (whisper_tensor.mojo:358-364), channels padded with zeros to C_in_pad.
-int convert_conv_weight(cudaStream_t st, const float *w, __nv_bfloat16 *dst, int C_out, int C_in, int C_in_pad);
+int convert_conv_weight(cudaStream_t st, const float *w, h16 *dst, int C_out, int C_in, int C_in_pad);
 
 }  // namespace wb

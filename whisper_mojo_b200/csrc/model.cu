@@ -165,8 +165,8 @@ int model_load(Model *m, const float *host, int64_t n_floats) {
     WB_CHECK(dalloc(m, &m->conv2_w, (size_t)D * 3 * D));
     WB_CHECK(convert_conv_weight(st, W + ly.conv1_w, m->conv1_w, D, m->NM, 128));
     WB_CHECK(convert_conv_weight(st, W + ly.conv2_w, m->conv2_w, D, D, D));
-    WB_CHECK(dalloc(m, &m->tok_emb_bf16, (size_t)m->V * D));
-    WB_CHECK(convert_f32_bf16(st, W + ly.tok_emb, m->tok_emb_bf16, (size_t)m->V * D));
+    WB_CHECK(dalloc(m, &m->tok_emb_h16, (size_t)m->V * D));
+    WB_CHECK(convert_f32_h16(st, W + ly.tok_emb, m->tok_emb_h16, (size_t)m->V * D));
     WB_CHECK(dalloc(m, &m->cross_wkv, (size_t)L * 2 * D * D));
     WB_CHECK(dalloc(m, &m->cross_bkv, (size_t)L * 2 * D));
     WB_CUDA(cudaMemsetAsync(m->cross_bkv, 0, (size_t)L * 2 * D * 4, st));
@@ -178,34 +178,34 @@ int model_load(Model *m, const float *host, int64_t n_floats) {
             const BlockW &b = side ? ly.dec[i] : ly.enc[i];
             LayerDev &d = side ? m->dec[i] : m->enc[i];
             WB_CHECK(dalloc(m, &d.wqkv, 3 * DD));
-            WB_CHECK(convert_f32_bf16(st, W + b.attn.q_w, d.wqkv, DD));
-            WB_CHECK(convert_f32_bf16(st, W + b.attn.k_w, d.wqkv + DD, DD));
-            WB_CHECK(convert_f32_bf16(st, W + b.attn.v_w, d.wqkv + 2 * DD, DD));
+            WB_CHECK(convert_f32_h16(st, W + b.attn.q_w, d.wqkv, DD));
+            WB_CHECK(convert_f32_h16(st, W + b.attn.k_w, d.wqkv + DD, DD));
+            WB_CHECK(convert_f32_h16(st, W + b.attn.v_w, d.wqkv + 2 * DD, DD));
             WB_CHECK(dalloc(m, &d.bqkv, (size_t)3 * D));
             WB_CUDA(cudaMemsetAsync(d.bqkv, 0, (size_t)3 * D * 4, st));
             WB_CUDA(cudaMemcpyAsync(d.bqkv, W + b.attn.q_b, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
             WB_CUDA(cudaMemcpyAsync(d.bqkv + 2 * D, W + b.attn.v_b, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
             WB_CHECK(dalloc(m, &d.wo, DD));
-            WB_CHECK(convert_f32_bf16(st, W + b.attn.o_w, d.wo, DD));
+            WB_CHECK(convert_f32_h16(st, W + b.attn.o_w, d.wo, DD));
             d.bo = W + b.attn.o_b;
             WB_CHECK(dalloc(m, &d.w1, (size_t)F * D));
-            WB_CHECK(convert_f32_bf16(st, W + b.fc1_w, d.w1, (size_t)F * D));
+            WB_CHECK(convert_f32_h16(st, W + b.fc1_w, d.w1, (size_t)F * D));
             WB_CHECK(dalloc(m, &d.w2, (size_t)F * D));
-            WB_CHECK(convert_f32_bf16(st, W + b.fc2_w, d.w2, (size_t)F * D));
+            WB_CHECK(convert_f32_h16(st, W + b.fc2_w, d.w2, (size_t)F * D));
             d.b1 = W + b.fc1_b, d.b2 = W + b.fc2_b;
             d.ln1_g = W + b.attn_ln_w, d.ln1_b = W + b.attn_ln_b;
             d.ln3_g = W + b.mlp_ln_w, d.ln3_b = W + b.mlp_ln_b;
             d.ln2_g = d.ln2_b = d.cbq = d.cbo = nullptr;
             if (side) {
                 WB_CHECK(dalloc(m, &d.cwq, DD));
-                WB_CHECK(convert_f32_bf16(st, W + b.cross.q_w, d.cwq, DD));
+                WB_CHECK(convert_f32_h16(st, W + b.cross.q_w, d.cwq, DD));
                 WB_CHECK(dalloc(m, &d.cwo, DD));
-                WB_CHECK(convert_f32_bf16(st, W + b.cross.o_w, d.cwo, DD));
+                WB_CHECK(convert_f32_h16(st, W + b.cross.o_w, d.cwo, DD));
                 d.cbq = W + b.cross.q_b, d.cbo = W + b.cross.o_b;
                 d.ln2_g = W + b.cross_ln_w, d.ln2_b = W + b.cross_ln_b;
                 // fused cross K/V projection: rows [(i*2+0)*D, +D) = Wk (no bias), [(i*2+1)*D, +D) = Wv (+bias)
-                WB_CHECK(convert_f32_bf16(st, W + b.cross.k_w, m->cross_wkv + (size_t)(i * 2) * DD, DD));
-                WB_CHECK(convert_f32_bf16(st, W + b.cross.v_w, m->cross_wkv + (size_t)(i * 2 + 1) * DD, DD));
+                WB_CHECK(convert_f32_h16(st, W + b.cross.k_w, m->cross_wkv + (size_t)(i * 2) * DD, DD));
+                WB_CHECK(convert_f32_h16(st, W + b.cross.v_w, m->cross_wkv + (size_t)(i * 2 + 1) * DD, DD));
                 WB_CUDA(cudaMemcpyAsync(m->cross_bkv + (size_t)(i * 2 + 1) * D, W + b.cross.v_b, (size_t)D * 4,
                                         cudaMemcpyDeviceToDevice, st));
                 if (cross_attn_absorbed_supported(D, m->H)) {
@@ -260,7 +260,7 @@ static int ensure_encoder_ws(Model *m, int n) {
     return WB_OK;
 }
 
-static GemmDesc plain_gemm(const bf16 *A, int M, int K, const bf16 *W, int N, const float *bias, int epi, void *out,
+static GemmDesc plain_gemm(const h16 *A, int M, int K, const h16 *W, int N, const float *bias, int epi, void *out,
                            int64_t out_ld) {
     GemmDesc g;
     g.A = A, g.lda = K, g.src_rows = M, g.Cin = K, g.rows_per_batch = M, g.batches = 1;
@@ -269,9 +269,9 @@ static GemmDesc plain_gemm(const bf16 *A, int M, int K, const bf16 *W, int N, co
     return g;
 }
 
-static int cross_kv_project(Model *m, const bf16 *enc_bf16, int n, Cache *c, int cache_off) {
+static int cross_kv_project(Model *m, const h16 *enc_h16, int n, Cache *c, int cache_off) {
     // out layout [L][2][B][S][D]; segment s = l*2+kv has stride B*S*D, rows are (chunk, position).
-    GemmDesc g = plain_gemm(enc_bf16, n * m->S, m->D, m->cross_wkv, m->L * 2 * m->D, m->cross_bkv, EPI_STORE_BF16,
+    GemmDesc g = plain_gemm(enc_h16, n * m->S, m->D, m->cross_wkv, m->L * 2 * m->D, m->cross_bkv, EPI_STORE_H16,
                             c->cross_kv + (size_t)cache_off * m->S * m->D, m->D);
     g.n_seg_ptrs = 0;
     g.seg_cols = m->D;
@@ -285,12 +285,12 @@ static int encode_batch(Model *m, const float *mel_dev, int n, float *enc_out_de
     cudaStream_t st = m->stream;
     const int D = m->D, S = m->S, NF = m->n_frames, M = n * S, impl = m->gemm_impl;
     const float *W = m->w32;
-    WB_CHECK(mel_to_bf16_T(st, mel_dev, m->e_melT, n, m->NM, NF));
+    WB_CHECK(mel_to_h16_T(st, mel_dev, m->e_melT, n, m->NM, NF));
     {  // conv1 + GELU (whisper.mojo:73-75) as a 3-tap implicit GEMM over [frames][128 padded channels]
         GemmDesc g;
         g.A = m->e_melT, g.a_batch_stride = (int64_t)NF * 128, g.lda = 128, g.src_rows = NF;
         g.conv_stride = 1, g.pad = 1, g.taps = 3, g.Cin = 128, g.batches = n, g.rows_per_batch = NF;
-        g.W = m->conv1_w, g.N = D, g.bias = W + m->lay.conv1_b, g.epi = EPI_GELU_BF16;
+        g.W = m->conv1_w, g.N = D, g.bias = W + m->lay.conv1_b, g.epi = EPI_GELU_H16;
         g.out[0] = m->e_x1T, g.out_ld[0] = D;
         WB_CHECK(gemm_run(st, g, impl));
     }
@@ -304,22 +304,22 @@ static int encode_batch(Model *m, const float *mel_dev, int n, float *enc_out_de
     }
     for (int l = 0; l < m->L; l++) {  // layers.mojo:435-519 with is_decoder = False
         const LayerDev &d = m->enc[l];
-        WB_CHECK(ln_bf16(st, m->e_x, d.ln1_g, d.ln1_b, M, D, m->e_xn, nullptr));
-        WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, m->e_qkv, 3 * D), impl));
+        WB_CHECK(ln_h16(st, m->e_x, d.ln1_g, d.ln1_b, M, D, m->e_xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_H16, m->e_qkv, 3 * D), impl));
         if (m->attn_impl) WB_CHECK(encoder_attention_tc(st, m->e_qkv, m->e_attn, n, S, m->H, D));
         else WB_CHECK(encoder_attention_ref(st, m->e_qkv, m->e_attn, n, S, m->H, D));
         WB_CHECK(gemm_run(st, plain_gemm(m->e_attn, M, D, d.wo, D, d.bo, EPI_RESID_F32, m->e_x, D), impl));
-        WB_CHECK(ln_bf16(st, m->e_x, d.ln3_g, d.ln3_b, M, D, m->e_xn, nullptr));
-        WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.w1, m->F, d.b1, EPI_GELU_BF16, m->e_h, m->F), impl));
+        WB_CHECK(ln_h16(st, m->e_x, d.ln3_g, d.ln3_b, M, D, m->e_xn, nullptr));
+        WB_CHECK(gemm_run(st, plain_gemm(m->e_xn, M, D, d.w1, m->F, d.b1, EPI_GELU_H16, m->e_h, m->F), impl));
         WB_CHECK(gemm_run(st, plain_gemm(m->e_h, M, m->F, d.w2, D, d.b2, EPI_RESID_F32, m->e_x, D), impl));
     }
     if (into && into->cross_impl == 1) {
         // absorbed form: the bf16 encoder output IS the cross-attention cache (one tensor for all layers)
-        WB_CHECK(ln_bf16(st, m->e_x, W + m->lay.enc_ln_w, W + m->lay.enc_ln_b, M, D,
+        WB_CHECK(ln_h16(st, m->e_x, W + m->lay.enc_ln_w, W + m->lay.enc_ln_b, M, D,
                          into->cross_enc + (size_t)cache_off * S * D, enc_out_dev));
         return WB_OK;
     }
-    WB_CHECK(ln_bf16(st, m->e_x, W + m->lay.enc_ln_w, W + m->lay.enc_ln_b, M, D, m->e_enc, enc_out_dev));
+    WB_CHECK(ln_h16(st, m->e_x, W + m->lay.enc_ln_w, W + m->lay.enc_ln_b, M, D, m->e_enc, enc_out_dev));
     if (into) WB_CHECK(cross_kv_project(m, m->e_enc, n, into, cache_off));
     return WB_OK;
 }
@@ -430,7 +430,7 @@ void cache_destroy(Cache *c) {
 int cache_reset(Cache *c) {
     Model *m = c->m;
     // the reference zero-fills its cache tensors (layers.mojo:30-36)
-    WB_CUDA(cudaMemsetAsync(c->self_kv, 0, (size_t)m->L * 2 * c->B * c->T * m->D * sizeof(bf16), m->stream));
+    WB_CUDA(cudaMemsetAsync(c->self_kv, 0, (size_t)m->L * 2 * c->B * c->T * m->D * sizeof(h16), m->stream));
     for (Lane &ln : c->lanes) WB_CHECK(greedy_init(m->stream, ln.g, ln.B, m->cfg.prompt));
     c->host_len = 0;
     c->has_cross = false;
@@ -442,14 +442,14 @@ int cache_set_encoder(Cache *c, const float *enc_out_dev) {
     WB_ARG(m->loaded, "kvcache_set_encoder before weights are loaded");
     const size_t per = (size_t)m->S * m->D;
     if (c->cross_impl == 1) {
-        WB_CHECK(convert_f32_bf16(m->stream, enc_out_dev, c->cross_enc, (size_t)c->B * per));
+        WB_CHECK(convert_f32_h16(m->stream, enc_out_dev, c->cross_enc, (size_t)c->B * per));
         c->has_cross = true;
         return WB_OK;
     }
     for (int i = 0; i < c->B; i += m->enc_batch) {
         int nb = std::min(m->enc_batch, c->B - i);
         WB_CHECK(ensure_encoder_ws(m, nb));
-        WB_CHECK(convert_f32_bf16(m->stream, enc_out_dev + i * per, m->e_enc, nb * per));
+        WB_CHECK(convert_f32_h16(m->stream, enc_out_dev + i * per, m->e_enc, nb * per));
         WB_CHECK(cross_kv_project(m, m->e_enc, nb, c, i));
     }
     c->has_cross = true;
@@ -493,7 +493,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     //  * split-K (tcgen05 path, batch large enough): the GEMM with M = batch and N = D only fills 32 CTAs and its K
     //    loop is what takes the time, so K is cut into slices that run as extra tiles (fp32 partials), and the
     //    LayerNorm kernel sums them into x in a fixed order first -- same number of launches, whole chip busy.
-    auto resid_gemm_ln = [&](int cat, const bf16 *A, int K, const bf16 *Wt, const float *bias, const float *g,
+    auto resid_gemm_ln = [&](int cat, const h16 *A, int K, const h16 *Wt, const float *bias, const float *g,
                              const float *bb) -> int {
         int split = 1;
         if (impl == GEMM_IMPL_TC && ln.part && (m->decode_split_k == 2 || (m->decode_split_k == 1 && B >= 512)))
@@ -512,16 +512,16 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
             return gemm_run(st, plain_gemm(A, B, K, Wt, D, bias, EPI_RESID_F32, ln.x, D), impl);
         }));
         if (!g) return WB_OK;
-        return timed_kernel(m, st, TK_LN, [&] { return ln_bf16(st, ln.x, g, bb, B, D, ln.xn, nullptr); });
+        return timed_kernel(m, st, TK_LN, [&] { return ln_h16(st, ln.x, g, bb, B, D, ln.xn, nullptr); });
     };
     for (int l = 0; l < m->L; l++) {
         const LayerDev &d = m->dec[l];
-        bf16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
-        bf16 *ck = c->cross_kv ? c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off : nullptr;
-        bf16 *cv = ck ? ck + cross_seg : nullptr;
+        h16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
+        h16 *ck = c->cross_kv ? c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off : nullptr;
+        h16 *cv = ck ? ck + cross_seg : nullptr;
         // (xn = LN1(x) was produced by embed_ln / by the previous layer's fc2 step)
         {  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
-            GemmDesc g = plain_gemm(ln.xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_BF16, ln.q, D);
+            GemmDesc g = plain_gemm(ln.xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_H16, ln.q, D);
             g.n_seg_ptrs = 3, g.seg_cols = D;
             g.out[1] = sk, g.out_ld[1] = (int64_t)c->T * D, g.dyn_mult[1] = D;
             g.out[2] = sv, g.out_ld[2] = (int64_t)c->T * D, g.dyn_mult[2] = D;
@@ -539,14 +539,14 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
             // absorbed form: q' = (Wk_h^T Wq_h) x + ..., attend over enc_out, out = (Wo Wv_h) ctx_h + ...
             const int HD = m->H * D;
             WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
-                return gemm_run(st, plain_gemm(ln.xn, B, D, d.wqk, HD, d.bqk, EPI_STORE_BF16, ln.qp, HD), impl);
+                return gemm_run(st, plain_gemm(ln.xn, B, D, d.wqk, HD, d.bqk, EPI_STORE_H16, ln.qp, HD), impl);
             }));
-            const bf16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
+            const h16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
             WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
             WB_CHECK(resid_gemm_ln(TK_CO, ln.ctx, HD, d.wov, d.bov, d.ln3_g, d.ln3_b));
         } else {
             WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
-                return gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_BF16, ln.q, D), impl);
+                return gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_H16, ln.q, D), impl);
             }));
             a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;
             a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
@@ -557,7 +557,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         // MLP (layers.mojo:490-517); the LayerNorm after fc2 is the next layer's attn_ln, or the decoder's ln_post
         // in front of the logits (whisper.mojo:156-158), or none on a prefill step
         WB_CHECK(timed_kernel(m, st, TK_FC1, [&] {
-            return gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_BF16, ln.h, m->F), impl);
+            return gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_H16, ln.h, m->F), impl);
         }));
         const bool last = l + 1 == m->L;
         const float *ng = last ? (with_logits ? W + m->lay.dec_ln_w : nullptr) : m->dec[l + 1].ln1_g;
@@ -565,7 +565,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         WB_CHECK(resid_gemm_ln(TK_FC2, ln.h, m->F, d.w2, d.b2, ng, nb));
     }
     if (with_logits) {  // whisper.mojo:156-166 + argmax :198,219
-        GemmDesc g = plain_gemm(ln.xn, B, D, m->tok_emb_bf16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
+        GemmDesc g = plain_gemm(ln.xn, B, D, m->tok_emb_h16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
         g.part_val = ln.part_val, g.part_idx = ln.part_idx;
         g.logits = (store_logits || impl == GEMM_IMPL_REF) ? ln.logits : nullptr;
         WB_ARG(!(store_logits || impl == GEMM_IMPL_REF) || ln.logits, "decode_step: cache has no logits buffer");
@@ -711,7 +711,7 @@ static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pc
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         size_t per_chunk = ((size_t)m->L * 2 * T_cache + (m->cross_impl == 1 ? (size_t)m->S : (size_t)m->L * 2 * m->S)) *
-                           m->D * sizeof(bf16);
+                           m->D * sizeof(h16);
         size_t cap = std::max<size_t>(1, (free_b / 2) / per_chunk);
         wave = (int)std::min<size_t>(wave, cap);
     }

@@ -1,6 +1,6 @@
 // model.h -- model-level state of the batched fast path (model.cu).
 #pragma once
-#include <cuda_bf16.h>
+#include "dtype.h"
 #include <cuda_runtime.h>
 
 #include <string>
@@ -11,7 +11,6 @@
 
 namespace wb {
 
-typedef __nv_bfloat16 bf16;
 
 struct AttnW {  // offsets (in floats) into the fp32 weight image; layers.mojo:96-103
     int64_t q_w, q_b, k_w, v_w, v_b, o_w, o_b;
@@ -33,9 +32,9 @@ struct Layout {  // export_weights.py:19-90
 Layout make_layout(const wm_config &c);
 
 struct LayerDev {
-    bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
-    bf16 *cwq = nullptr, *cwo = nullptr;  // decoder cross-attention
-    bf16 *wqk = nullptr, *wov = nullptr;  // folded cross projections [H*D][D], [D][H*D] (absorbed form)
+    h16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    h16 *cwq = nullptr, *cwo = nullptr;  // decoder cross-attention
+    h16 *wqk = nullptr, *wov = nullptr;  // folded cross projections [H*D][D], [D][H*D] (absorbed form)
     float *bqk = nullptr, *bov = nullptr;
     float *bqkv = nullptr;                // [3D]: q bias, zeros (k has no bias), v bias
     const float *bo, *b1, *b2, *cbq, *cbo;
@@ -67,14 +66,14 @@ struct Model {
     Layout lay;
     float *w32 = nullptr;
     bool loaded = false;
-    bf16 *conv1_w = nullptr, *conv2_w = nullptr, *tok_emb_bf16 = nullptr, *cross_wkv = nullptr;
+    h16 *conv1_w = nullptr, *conv2_w = nullptr, *tok_emb_h16 = nullptr, *cross_wkv = nullptr;
     float *cross_bkv = nullptr;
     std::vector<LayerDev> enc, dec;
     FrontendTables ft;
     std::vector<void *> owned;
     // encoder workspace (sized for enc_cap chunks)
     int enc_cap = 0;
-    bf16 *e_melT = nullptr, *e_x1T = nullptr, *e_xn = nullptr, *e_qkv = nullptr, *e_attn = nullptr, *e_h = nullptr,
+    h16 *e_melT = nullptr, *e_x1T = nullptr, *e_xn = nullptr, *e_qkv = nullptr, *e_attn = nullptr, *e_h = nullptr,
          *e_enc = nullptr;
     float *e_x = nullptr;
     float timing[5] = {0, 0, 0, 0, 0};
@@ -96,7 +95,7 @@ struct Model {
 struct Lane {
     int B = 0, b_off = 0;
     float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr, *part = nullptr;
-    bf16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *qp = nullptr, *ctx = nullptr;
+    h16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *qp = nullptr, *ctx = nullptr;
     int *part_idx = nullptr, *next = nullptr;
     int cross_splits = 1;
     GreedyState g;  // per-chunk arrays point into the cache-wide arrays at b_off; scalars are per lane
@@ -107,9 +106,9 @@ struct Cache {
     int B = 0, T = 0;
     int host_len = 0;  // mirror of current_len for the step-wise API
     bool has_cross = false;
-    bf16 *self_kv = nullptr;   // [L][2][B][T][D]
-    bf16 *cross_kv = nullptr;  // [L][2][B][S][D]   (cross_impl 0)
-    bf16 *cross_enc = nullptr; // [B][S][D]        (cross_impl 1: enc_out itself, shared by all layers)
+    h16 *self_kv = nullptr;   // [L][2][B][T][D]
+    h16 *cross_kv = nullptr;  // [L][2][B][S][D]   (cross_impl 0)
+    h16 *cross_enc = nullptr; // [B][S][D]        (cross_impl 1: enc_out itself, shared by all layers)
     int cross_impl = 0;
     int *tokens_out = nullptr, *out_len = nullptr, *cur_tok = nullptr, *done = nullptr, *scalars = nullptr;
     std::vector<Lane> lanes;

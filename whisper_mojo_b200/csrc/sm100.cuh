@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dtype.h"
+
 namespace wb {
 namespace ptx {
 
@@ -129,7 +131,7 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, one CTA.
-__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void mma_h16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -223,7 +225,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 }
 // D[tmem of both CTAs] (+)= A * B with M = 256 split over the pair (128 rows each) and the N columns of B
 // split over the pair's shared memories (N/2 rows each); issued by one thread of the leader CTA.
-__device__ __forceinline__ void mma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void mma_h16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                  uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -263,9 +265,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
     return d;
 }
-// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M x N tile, operand majors (0 = K, 1 = MN).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// Instruction descriptor, kind::f16: h16 x h16 -> fp32 (a / b format field: 0 = fp16, 1 = bf16; dtype.h), M x N tile,
+// operand majors (0 = K, 1 = MN).
+__host__ __device__ constexpr uint32_t umma_idesc_h16(int M, int N, int a_mn_major, int b_mn_major) {
+    constexpr uint32_t fmt = H16_IS_FP16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

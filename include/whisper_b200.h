@@ -115,7 +115,19 @@ typedef uint64_t wm_cache;
 /* Whisper() (whisper.mojo:175-178).  `stream` = a cudaStream_t to enqueue on, or NULL for a
  * library-owned stream on the current device. */
 int wm_create(const wm_config *cfg, void *stream, wm_model *out);
+/* Fails with WB_ERR_ARG while wm_kvcache handles of the model are alive (destroy those first). */
 int wm_destroy(wm_model m);
+/* Stream ordering.  Every wm_* call enqueues on the model's stream (the one passed to wm_create, else a
+ * library-owned non-blocking stream).  Entry points that return HOST data synchronise it; the *_dev entry points
+ * (wm_logmel_dev, wm_encode_dev, wm_kvcache_set_encoder_dev) return with work still queued and READ their inputs on
+ * that stream: a caller that produces inputs or consumes outputs on another stream must order the two -- get the
+ * stream with wm_stream and use events, or call wm_synchronize (wm_transcribe*_dev synchronise before returning).
+ * Host buffers may be pageable or pinned; pinned (cudaMallocHost / cudaHostRegister) buffers make the uploads of
+ * wm_transcribe / wm_transcribe_pcm asynchronous DMA that fully overlaps the compute, pageable ones are staged by
+ * the driver one encoder sub-batch at a time (still overlapped with the previous sub-batch's compute, but the
+ * PCIe copy then bounds the call; see DESIGN.md section 6 for both numbers). */
+int wm_stream(wm_model m, void **stream);
+int wm_synchronize(wm_model m);
 /* Number of fp32 values the flat weight file must hold for this config (export_weights.py:19-90). */
 int64_t wm_weight_count(const wm_config *cfg);
 /* Whisper.load(WeightLoader(path)) (loader.mojo:10-27, whisper.mojo:180-182): validates the byte

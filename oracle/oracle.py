@@ -76,6 +76,7 @@ def lib():
         L.wo_transcribe.restype = c_int
         L.wo_teacher_forced.argtypes = [c_void_p, PF, PI, c_int, c_int, PF]
         L.wo_num_threads.restype = c_int
+        L.wo_set_num_threads.argtypes = [c_int]
         _lib = L
     return _lib
 
@@ -201,3 +202,8 @@ class OracleWhisper:
 
 def num_threads() -> int:
     return int(lib().wo_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the oracle's parallel loops (the CPU arms of bench.py set this explicitly)."""
+    lib().wo_set_num_threads(int(n))

@@ -714,3 +714,13 @@ int wo_num_threads(void) {
     return 1;
 #endif
 }
+
+/* Explicit thread count for the timed CPU arms (bench.py): launchers such as torch.distributed.run export
+ * OMP_NUM_THREADS=1 to their workers, which would silently serialise the parallelize() analogues above. */
+void wo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -493,3 +493,71 @@ def test_small_batch_latency_path_matches_oracle():
         assert ok, (i, msg)
     again, again_len = m.transcribe_batch(mel)  # 12 > small_batch: the default path, bit-identical to before
     assert np.array_equal(again, base) and np.array_equal(again_len, base_len)
+
+
+def test_config_limits_are_rejected_at_create():
+    """The greedy loop writes K/V rows up to 3 + max_iters and embeds positions up to 4 + max_iters: a config whose
+    loop would run past n_text_ctx (or with more heads than the decode attention kernel has warps) must be refused
+    by wm_create, not corrupt the next chunk's cache."""
+    base = WhisperConfig.micro()
+    with pytest.raises(_lib.WhisperB200Error) as e:
+        Whisper(WhisperConfig(**{**base.__dict__, "max_iters": base.n_text_ctx - 4}))
+    assert e.value.code == _lib.WB_ERR_ARG and "max_iters" in str(e.value)
+    Whisper(WhisperConfig(**{**base.__dict__, "max_iters": base.n_text_ctx - 5}))  # the largest legal loop
+    with pytest.raises(_lib.WhisperB200Error) as e:
+        Whisper(WhisperConfig(d_model=1024, n_heads=16, n_layers=2))
+    assert "n_heads" in str(e.value)
+
+
+def test_two_models_on_two_threads_do_not_interfere():
+    """several model instances per process must be safe.  Two models with different per-model options
+    (programmatic dependent launch on / off, small_batch on / off) transcribe concurrently from two host threads;
+    each must reproduce its own single-threaded ids."""
+    import threading
+
+    cfg = WhisperConfig.micro()
+    ma, _ = build(cfg, pdl=1, small_batch=8)
+    mb, _ = build(cfg)
+    mel_a, mel_b = synth.make_mel(5, cfg, 31), synth.make_mel(40, cfg, 32)
+    ref_a, ref_b = ma.transcribe_batch(mel_a)[0], mb.transcribe_batch(mel_b)[0]
+    out, err = {}, []
+
+    def work(name, m, mel):
+        try:
+            out[name] = [m.transcribe_batch(mel)[0] for _ in range(6)]
+        except Exception as ex:  # pragma: no cover
+            err.append(ex)
+
+    ts = [threading.Thread(target=work, args=("a", ma, mel_a)), threading.Thread(target=work, args=("b", mb, mel_b))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not err, err
+    assert all(np.array_equal(t, ref_a) for t in out["a"]) and all(np.array_equal(t, ref_b) for t in out["b"])
+
+
+def test_destroying_a_model_with_live_caches_is_refused():
+    cfg = WhisperConfig.micro()
+    m, _ = build(cfg)
+    cache = DeviceKVCache(m, 2, 16)
+    rc = _lib.load().wm_destroy(m._h)
+    assert rc == _lib.WB_ERR_ARG and "kvcache" in _lib.last_error()
+    del cache  # wm_kvcache_destroy
+    assert _lib.load().wm_destroy(m._h) == _lib.WB_OK
+    m._h = 0
+
+
+def test_pageable_and_pinned_host_buffers_give_the_same_ids():
+    """wm_transcribe_pcm accepts any host pointer: pinned memory makes the sub-batch uploads asynchronous DMA, pageable
+    memory is staged by the driver; ids must not depend on it (3 encoder sub-batches so the uploads interleave)."""
+    cfg = WhisperConfig.micro()
+    m, _ = build(cfg, enc_batch=2)
+    a = synth.make_audio(5, cfg, seed=3)
+    t0, l0 = m.transcribe_pcm_batch(a)  # pageable numpy
+    pinned = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+    pinned.copy_(torch.from_numpy(a))
+    t1, l1 = m.transcribe_pcm_batch(pinned.numpy())
+    assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
+    td, ld = m.transcribe_pcm_batch(torch.from_numpy(a).cuda())
+    assert np.array_equal(td.cpu().numpy(), t0)

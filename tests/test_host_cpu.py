@@ -136,6 +136,30 @@ def test_bench_reference_arm_contract():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: rank 0 of the reference arm must still use
+    # every host core (round 1's arm timed out at N > 1 for this reason)
+    r3 = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                        env={**os.environ, "RANK": "0", "WORLD_SIZE": "2", "OMP_NUM_THREADS": "1"})
+    assert r3.returncode == 0, r3.stderr[-2000:]
+    d3 = json.loads([ln for ln in r3.stdout.splitlines() if ln.strip()][0])
+    assert d3["cpu_baseline"]["cores"] == max(1, len(os.sched_getaffinity(0)))
     if not torch.cuda.is_available():
         r2 = subprocess.run([sys.executable, bench, "--steps", "1"], capture_output=True, text=True, timeout=600)
         assert r2.returncode != 0 and "no CUDA device" in (r2.stderr + r2.stdout)
+
+
+def test_bench_chunk_audio_depends_only_on_the_global_index():
+    """bench.py shards ONE global seeded batch: chunk i's samples must not depend on the shard it is generated in,
+    otherwise ids could not be compared across GPU counts (strong scaling)."""
+    import importlib.util
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    dev = torch.device("cpu")
+    full = b.synth_pcm_gpu(0, 192, 1600, dev, 7)
+    for lo, hi in ((0, 96), (96, 192), (64, 128), (130, 131)):
+        assert torch.equal(b.synth_pcm_gpu(lo, hi, 1600, dev, 7), full[lo:hi]), (lo, hi)
+    assert not torch.equal(full[0], full[64])

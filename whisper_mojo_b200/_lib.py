@@ -54,6 +54,8 @@ SIGNATURES = {
     "wt_transpose": (c_int, [c_uint64, c_uint64]),
     "wm_create": (c_int, [c_void_p, c_void_p, POINTER(c_uint64)]),
     "wm_destroy": (c_int, [c_uint64]),
+    "wm_stream": (c_int, [c_uint64, POINTER(c_void_p)]),
+    "wm_synchronize": (c_int, [c_uint64]),
     "wm_weight_count": (c_int64, [c_void_p]),
     "wm_load_weights_file": (c_int, [c_uint64, c_char_p]),
     "wm_load_weights": (c_int, [c_uint64, c_void_p, c_int64]),

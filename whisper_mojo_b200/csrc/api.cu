@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -15,7 +16,7 @@
 namespace wb {
 
 std::atomic<int64_t> g_launches{0};
-bool g_pdl = false;  // programmatic dependent launch of the decode-step kernels: measured, no gain
+thread_local bool g_pdl = false;  // programmatic dependent launch of the launches this thread makes (see PdlScope)
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -23,6 +24,21 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
+}
+
+cudaError_t ensure_dyn_smem_impl(const void *func, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, int> opted;
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    int &cur = opted[{dev, func}];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
 }
 
 struct TensorH {
@@ -77,9 +93,24 @@ using namespace wb;
 #define TENSOR(var, h)                                  \
     TensorH *var = get(g_tensors, h);                   \
     WB_ARG(var != nullptr, "bad tensor handle %llu", (unsigned long long)(h))
-#define MODEL(var, h)                                  \
-    Model *var = get(g_models, h);                     \
-    WB_ARG(var != nullptr, "bad model handle %llu", (unsigned long long)(h))
+// Every model-level entry point runs with the model's device current and the model's own programmatic-dependent-
+// launch setting (both restored on return): several models, one per device, are safe in one process.
+struct DeviceScope {
+    int saved = -1;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&saved) != cudaSuccess) saved = -1;
+        if (saved != dev) cudaSetDevice(dev);
+        else saved = -1;
+    }
+    ~DeviceScope() {
+        if (saved >= 0) cudaSetDevice(saved);
+    }
+};
+#define MODEL(var, h)                                                                \
+    Model *var = get(g_models, h);                                                   \
+    WB_ARG(var != nullptr, "bad model handle %llu", (unsigned long long)(h));        \
+    DeviceScope dev_scope__(var->device);                                            \
+    PdlScope pdl_scope__(var->pdl)
 #define CACHE(var, h)                                  \
     Cache *var = get(g_caches, h);                     \
     WB_ARG(var != nullptr, "bad cache handle %llu", (unsigned long long)(h))
@@ -319,8 +350,16 @@ int wm_create(const wm_config *cfg, void *stream, wm_model *out) {
 
 int wm_destroy(wm_model h) {
     if (h == 0) return WB_OK;
+    {
+        Model *live = get(g_models, h);
+        WB_ARG(live != nullptr, "bad model handle");
+        // caches hold a pointer to their model (streams, weights): destroying the model first would leave them dangling
+        WB_ARG(live->n_caches == 0, "wm_destroy: %d wm_kvcache handle(s) of this model are still alive; destroy them first",
+               live->n_caches);
+    }
     Model *m = take(g_models, h);
     WB_ARG(m != nullptr, "bad model handle");
+    DeviceScope ds(m->device);
     model_destroy(m);
     return WB_OK;
 }
@@ -382,7 +421,14 @@ int wm_weight_tensor(wm_model h, int index, void **dev_ptr, int64_t *n_floats) {
 int wm_set_option(wm_model h, const char *key, int64_t value) {
     MODEL(m, h);
     WB_ARG(key, "null key");
-    if (!strcmp(key, "gemm_impl")) m->gemm_impl = (int)value;
+    if (!strcmp(key, "gemm_impl")) {
+        WB_ARG(value >= GEMM_IMPL_REF && value <= GEMM_IMPL_TC_PAIR, "gemm_impl must be 0..3");
+        if (m->gemm_impl != (int)value && m->tr_cache) {  // the captured decode graph holds the old kernels
+            cache_destroy(m->tr_cache);
+            m->tr_cache = nullptr;
+        }
+        m->gemm_impl = (int)value;
+    }
     else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
     else if (!strcmp(key, "frontend_impl")) m->frontend_impl = (int)value;
     else if (!strcmp(key, "decode_split_k")) {
@@ -393,8 +439,8 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
             m->tr_cache = nullptr;
         }
     }
-    else if (!strcmp(key, "pdl")) {  // process-wide; captured decode graphs keep the setting they were built with
-        g_pdl = value != 0;
+    else if (!strcmp(key, "pdl")) {  // per model; captured decode graphs keep the setting they were built with
+        m->pdl = value != 0;
         if (m->tr_cache) {
             cache_destroy(m->tr_cache);
             m->tr_cache = nullptr;
@@ -503,6 +549,7 @@ int wm_kvcache_create(wm_model h, int n_chunks, int max_len, wm_cache *out) {
     WB_ARG(out, "kvcache_create: null out");
     Cache *c = nullptr;
     WB_CHECK(cache_create(m, n_chunks, max_len, true, 1, &c));
+    m->n_caches++;
     *out = put(g_caches, c);
     return WB_OK;
 }
@@ -510,6 +557,8 @@ int wm_kvcache_destroy(wm_cache h) {
     if (h == 0) return WB_OK;
     Cache *c = take(g_caches, h);
     WB_ARG(c != nullptr, "bad cache handle");
+    DeviceScope ds(c->m->device);
+    c->m->n_caches--;
     cache_destroy(c);
     return WB_OK;
 }
@@ -591,6 +640,18 @@ int wm_teacher_forced(wm_model h, const float *enc_out_dev, int n_chunks, const 
             WB_ARG(forced_host[i] >= 0 && forced_host[i] < m->V, "teacher_forced: token id %d out of range",
                    forced_host[i]);
     return model_teacher_forced(m, enc_out_dev, n_chunks, forced_host, n_forced, logits_host);
+}
+
+int wm_stream(wm_model h, void **stream) {
+    MODEL(m, h);
+    WB_ARG(stream, "null out");
+    *stream = reinterpret_cast<void *>(m->stream);
+    return WB_OK;
+}
+int wm_synchronize(wm_model h) {
+    MODEL(m, h);
+    WB_CUDA(cudaStreamSynchronize(m->stream));
+    return WB_OK;
 }
 
 int wm_last_timing(wm_model h, float ms[5]) {

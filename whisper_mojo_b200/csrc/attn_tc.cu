@@ -291,12 +291,7 @@ static int launch_attn(cudaStream_t st, AttnTcParams &P, const h16 *qkv, int B, 
     WB_CHECK(make_tmap_h16(&P.kv_map, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, (uint64_t)3 * D, (uint64_t)S * 3 * D,
                             KB, 3));
     P.n_kblocks = cdiv(S, KB);
-    static bool opted = false;
-    if (!opted) {
-        WB_CUDA(cudaFuncSetAttribute(encoder_attn_tc_kernel<KB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     AttCfg<KB>::SMEM));
-        opted = true;
-    }
+    WB_CUDA(ensure_dyn_smem(encoder_attn_tc_kernel<KB, DBG>, AttCfg<KB>::SMEM));
     dim3 grid(cdiv(S, 128), H, B);
     encoder_attn_tc_kernel<KB, DBG><<<grid, ATT_THREADS, AttCfg<KB>::SMEM, st>>>(P);
     WB_LAUNCHED();

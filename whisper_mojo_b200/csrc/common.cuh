@@ -51,12 +51,28 @@ extern std::atomic<int64_t> g_launches;
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device.  The attribute is per device and per
+// kernel, so the cache is keyed by both; it only ever grows (a smaller request never lowers the limit another model
+// in the process relies on).  Returns a cudaError_t.
+cudaError_t ensure_dyn_smem_impl(const void *func, int bytes);
+template <typename K>
+static inline cudaError_t ensure_dyn_smem(K kernel, size_t bytes) {
+    return ensure_dyn_smem_impl(reinterpret_cast<const void *>(kernel), (int)bytes);
+}
+
 // Programmatic dependent launch (option "pdl", default off: measured 432 vs 431 ms of decode, i.e. the captured
 // graph already hides launch latency): the kernels of the decode step are launched with programmatic
 // stream serialisation, so kernel N+1's CTAs are scheduled -- and run their prologue (barrier init, TMEM
 // allocation, tensor-map prefetch) -- while kernel N still executes; every such kernel executes pdl_wait()
 // before its first access to memory a predecessor may write.  Without the attribute both instructions are no-ops.
-extern bool g_pdl;
+// Per thread, set from the model's own `pdl` field at every model-level entry point (PdlScope): two models driven
+// from two host threads never see each other's setting.
+extern thread_local bool g_pdl;
+struct PdlScope {
+    bool saved;
+    explicit PdlScope(bool on) : saved(g_pdl) { g_pdl = on; }
+    ~PdlScope() { g_pdl = saved; }
+};
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args &&...args) {

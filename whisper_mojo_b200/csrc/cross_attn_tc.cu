@@ -504,12 +504,8 @@ int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = pair ? 2 * std::min(B, sms / 2) : (B < sms ? B : sms);
-    static bool opted[8] = {false, false, false, false, false, false, false, false};
-    auto launch = [&](auto kernel, int slot) {
-        if (!opted[slot]) {
-            WB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            opted[slot] = true;
-        }
+    auto launch = [&](auto kernel, int) {
+        WB_CUDA(ensure_dyn_smem(kernel, smem));
         WB_CUDA(launch_pdl(kernel, dim3(grid), dim3(XA_THREADS), smem, st, P));
         WB_LAUNCHED();
         return WB_OK;

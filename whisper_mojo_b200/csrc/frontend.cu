@@ -284,11 +284,7 @@ int logmel_raw(cudaStream_t st, FrontendTables &t, const float *pcm, int B, int 
     WB_LAUNCHED();
     if (impl == 1 && t.tc_ok) return logmel_raw_tc(st, t, pcm, B, n_frames, mel_raw, chunk_max_enc);
     const size_t smem = (size_t)(SEG + 2 * NFOLD * FR + FR) * sizeof(float);
-    static bool opted = false;
-    if (!opted) {
-        WB_CUDA(cudaFuncSetAttribute(logmel_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        opted = true;
-    }
+    WB_CUDA(ensure_dyn_smem(logmel_raw_kernel, smem));
     static_assert(2 * NFOLD * FR >= FR * 204, "power tile must fit in the folded-sample buffers");
     dim3 grid(cdiv(n_frames, FR), B);
     logmel_raw_kernel<<<grid, 256, smem, st>>>(pcm, n_frames, t.tw_cos, t.tw_sin, t.window, t.mel_w, t.mel_start,

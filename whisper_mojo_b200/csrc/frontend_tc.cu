@@ -358,11 +358,7 @@ int logmel_raw_tc(cudaStream_t st, FrontendTables &t, const float *pcm, int B, i
     P.n_frames = n_frames, P.n_mels = t.n_mels;
     P.tiles_per_chunk = cdiv(n_frames, 256);
     P.total_tiles = B * P.tiles_per_chunk;
-    static bool opted = false;
-    if (!opted) {
-        WB_CUDA(cudaFuncSetAttribute(logmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-        opted = true;
-    }
+    WB_CUDA(ensure_dyn_smem(logmel_tc_kernel, FT_SMEM));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

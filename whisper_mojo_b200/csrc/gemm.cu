@@ -744,11 +744,7 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 template <int EPI>
 static int launch_tc(cudaStream_t st, const GemmTcParams &P, int grid) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        WB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr_set = true;
-    }
+    WB_CUDA(ensure_dyn_smem(gemm_tc_kernel<EPI>, TC_SMEM_BYTES));
     WB_CUDA(launch_pdl(gemm_tc_kernel<EPI>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, st, P));
     WB_LAUNCHED();
     return WB_OK;
@@ -756,12 +752,8 @@ static int launch_tc(cudaStream_t st, const GemmTcParams &P, int grid) {
 
 template <int EPI, int BN2, bool TMA_OUT>
 static int launch_pair(cudaStream_t st, const GemmPairParams &P, int grid) {
-    static bool attr_set = false;
     constexpr int smem = pair_smem_bytes(TMA_OUT);
-    if (!attr_set) {
-        WB_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BN2, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    WB_CUDA(ensure_dyn_smem(gemm_pair_kernel<EPI, BN2, TMA_OUT>, smem));
     WB_CUDA(launch_pdl(gemm_pair_kernel<EPI, BN2, TMA_OUT>, dim3(grid), dim3(TC_THREADS), smem, st, P));
     WB_LAUNCHED();
     return WB_OK;

@@ -305,8 +305,7 @@ int decode_attention_splits(int B, int len, int H) {
         int chunk = ((len + s - 1) / s + 3) & ~3;
         // resident CTAs per SM for this shared-memory footprint, from the occupancy calculator
         size_t smem = (size_t)H * (chunk + 4) * sizeof(float);
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_dyn_smem(decode_attn_kernel, smem);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel, H * 32, smem) != cudaSuccess)
             per_sm = 4, cudaGetLastError();
@@ -333,11 +332,7 @@ int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {
     int chunk = (a.max_len + a.splits - 1) / a.splits;
     p.smem_len = ((chunk + 3) & ~3) + 4;
     size_t smem = (size_t)a.H * p.smem_len * sizeof(float);
-    static size_t smem_opted = 48 * 1024;
-    if (smem > smem_opted) {
-        WB_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_opted = smem;
-    }
+    WB_CUDA(ensure_dyn_smem(decode_attn_kernel, smem));
     dim3 grid(a.B, a.splits);
     WB_CUDA(launch_pdl(decode_attn_kernel, grid, dim3(a.H * 32), smem, st, p));
     WB_LAUNCHED();
@@ -393,11 +388,7 @@ __global__ void __launch_bounds__(256) encoder_attn_ref_kernel(const h16 *__rest
 int encoder_attention_ref(cudaStream_t st, const h16 *qkv, h16 *out, int B, int S, int H, int D) {
     if (B <= 0) return WB_OK;
     size_t smem = (size_t)8 * S * sizeof(float);
-    static size_t smem_opted = 48 * 1024;
-    if (smem > smem_opted) {
-        WB_CUDA(cudaFuncSetAttribute(encoder_attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_opted = smem;
-    }
+    WB_CUDA(ensure_dyn_smem(encoder_attn_ref_kernel, smem));
     dim3 grid(cdiv(S, 8), H, B);
     encoder_attn_ref_kernel<<<grid, 256, smem, st>>>(qkv, out, S, H, D);
     WB_LAUNCHED();

@@ -86,13 +86,20 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
     WB_ARG(cfg->n_mels > 0 && cfg->n_mels <= 128 && cfg->n_layers > 0 && cfg->vocab_size > 0 &&
                cfg->n_audio_ctx > 0 && cfg->n_text_ctx >= 8 && cfg->max_iters >= 0,
            "wm_create: bad config");
+    // the greedy loop writes K/V rows 0 .. 3 + max_iters and embeds positions up to 4 + max_iters (whisper.mojo:193
+    // sizes the reference's cache at 448 for 4 + 195 rows): a longer loop would run past the cache
+    WB_ARG(cfg->max_iters + 5 <= cfg->n_text_ctx, "wm_create: max_iters %d + 5 exceeds n_text_ctx %d", cfg->max_iters,
+           cfg->n_text_ctx);
+    // decode self-attention runs one warp per head in one CTA (kernels.cu: decode_attn_kernel, 12 warps)
+    WB_ARG(cfg->n_heads <= 12, "wm_create: n_heads %d > 12 is not supported by the decode attention kernel", cfg->n_heads);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("wm_create: no CUDA device (this library has no CPU fallback)");
         return WB_ERR_CUDA;
     }
-    if (const char *e = getenv("WB_PDL")) g_pdl = atoi(e) != 0;  // A/B switch for programmatic dependent launch
     Model *m = new Model();
+    if (const char *e = getenv("WB_PDL")) m->pdl = atoi(e) != 0;  // A/B switch for programmatic dependent launch
+    cudaGetDevice(&m->device);
     m->cfg = *cfg;
     m->D = cfg->d_model, m->H = cfg->n_heads, m->L = cfg->n_layers, m->V = cfg->vocab_size;
     m->S = cfg->n_audio_ctx, m->T = cfg->n_text_ctx, m->NM = cfg->n_mels, m->F = 4 * cfg->d_model;
@@ -686,10 +693,10 @@ int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n
                      int32_t *out_len_dev, const float *in_host) {
     const bool small = m->small_batch > 0 && n > 0 && std::min(n, m->wave_max) <= m->small_batch && m->cross_impl == 1;
     const int saved_impl = m->cross_impl;
-    const bool saved_pdl = g_pdl;
-    if (small) m->cross_impl = 0, g_pdl = true;
+    PdlScope pdl(small || m->pdl);  // this thread's launches only
+    if (small) m->cross_impl = 0;
     const int rc = model_transcribe_impl(m, mel_dev, pcm_dev, n, out_tokens_dev, out_len_dev, in_host);
-    m->cross_impl = saved_impl, g_pdl = saved_pdl;
+    m->cross_impl = saved_impl;
     return rc;
 }
 
@@ -726,12 +733,20 @@ static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pc
         // the staging buffer may still be read by work queued earlier on the compute stream
         WB_CUDA(cudaEventRecord(m->ev_plain[subs.size()], st));
         WB_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_plain[subs.size()], 0));
-        for (size_t k = 0; k < subs.size(); k++) {
-            const size_t off = (size_t)subs[k].first * in_per, cnt = (size_t)subs[k].second * in_per;
-            WB_CUDA(cudaMemcpyAsync(in_dev + off, in_host + off, cnt * 4, cudaMemcpyHostToDevice, m->stream2));
-            WB_CUDA(cudaEventRecord(m->ev_plain[k], m->stream2));
-        }
     }
+    // Upload of sub-batch k on the copy stream.  Sub-batch 0 goes first, and sub-batch k + 1 is issued right after
+    // the compute of sub-batch k has been queued: with pinned host memory every copy is an asynchronous DMA and the
+    // order of issue does not matter; with PAGEABLE memory cudaMemcpyAsync stages through the driver and blocks the
+    // host until the slice is staged, so issuing all slices up front would keep the GPU idle for the whole transfer,
+    // while this order hides each slice's staging under the previous slice's frontend + encoder.
+    auto upload = [&](size_t k) -> int {
+        if (!in_host || k >= subs.size()) return WB_OK;
+        const size_t off = (size_t)subs[k].first * in_per, cnt = (size_t)subs[k].second * in_per;
+        WB_CUDA(cudaMemcpyAsync(in_dev + off, in_host + off, cnt * 4, cudaMemcpyHostToDevice, m->stream2));
+        WB_CUDA(cudaEventRecord(m->ev_plain[k], m->stream2));
+        return WB_OK;
+    };
+    WB_CHECK(upload(0));
     if (!mel_dev && m->tr_mel_cap < (size_t)std::min(eb, n) * mel_per) {  // log-mel of one sub-batch
         cudaFree(m->tr_mel);
         m->tr_mel = nullptr, m->tr_mel_cap = 0;
@@ -765,6 +780,7 @@ static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pc
             cudaEventRecord(m->ev_timed[3 * k + 1], st);
             if (rc == WB_OK) rc = encode_batch(m, mel_s, ns, nullptr, c, i - w0);
             cudaEventRecord(m->ev_timed[3 * k + 2], st);
+            if (rc == WB_OK) rc = upload(k + 1);
         }
         if (rc != WB_OK) break;
         c->has_cross = true;

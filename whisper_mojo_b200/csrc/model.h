@@ -58,6 +58,9 @@ struct Model {
     cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: host->device uploads, second decode lane
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
+    bool pdl = false;  // programmatic dependent launch of the decode-step kernels (option "pdl"; env WB_PDL at create)
+    int device = 0;    // the CUDA device the model was created on; entry points make it current (DeviceScope)
+    int n_caches = 0;  // live wm_kvcache handles (wm_destroy refuses while any exist)
     int gemm_impl = 1, attn_impl = 1, frontend_impl = 1,  // frontend: 0 = fp32 FMA DFT, 1 = TF32x3 tensor-core DFT
          use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048, small_batch = 0,
         decode_split_k = 1,  // split-K residual GEMMs + fused residual/LayerNorm in the decode step

@@ -119,6 +119,9 @@ class DeviceKVCache:
         return n.value
 
     def set_encoder(self, enc_out_dev_ptr: int) -> None:
+        """enc_out f32 [n_chunks, ctx, d_model] on the device (raw pointer).  The model's stream is ordered after
+        torch's current stream first, so a tensor still being produced there is not read early."""
+        self._model._order_after_torch()
         _lib.check(_lib.load().wm_kvcache_set_encoder_dev(self._model._h, self._h, c_void_p(enc_out_dev_ptr)))
 
     def reset(self) -> None:
@@ -176,6 +179,25 @@ class Whisper:
     def set_option(self, key: str, value: int) -> None:
         _lib.check(_lib.load().wm_set_option(self._h, key.encode(), int(value)))
 
+    def stream_ptr(self) -> int:
+        """cudaStream_t the model enqueues on (wm_stream)."""
+        p = c_void_p(0)
+        _lib.check(_lib.load().wm_stream(self._h, ctypes.byref(p)))
+        return p.value or 0
+
+    def synchronize(self) -> None:
+        _lib.check(_lib.load().wm_synchronize(self._h))
+
+    def _order_after_torch(self, device=None) -> None:
+        """Make the model's stream wait for everything queued so far on torch's current stream (CUDA-tensor inputs may
+        still be in flight there; the library runs on its own non-blocking stream unless one was passed to Whisper())."""
+        import torch
+
+        cur = torch.cuda.current_stream(device)
+        ptr = self.stream_ptr()
+        if ptr != cur.cuda_stream:
+            torch.cuda.ExternalStream(ptr, device=cur.device).wait_stream(cur)
+
     # ---- main.mojo's call ------------------------------------------------------------------
     def transcribe(self, mel) -> List[int]:
         """transcribe(mel: Tensor[80, 3000]) -> List[Int] (whisper.mojo:184-223)."""
@@ -221,6 +243,7 @@ class Whisper:
             n = mel.shape[0]
             toks = torch.empty((n, c.max_tokens), dtype=torch.int32, device=mel.device)
             lens = torch.empty((n,), dtype=torch.int32, device=mel.device)
+            self._order_after_torch(mel.device)  # wm_transcribe*_dev synchronise before returning: outputs are ready
             _lib.check(lib.wm_transcribe_dev(self._h, c_void_p(mel.data_ptr()), n, c_void_p(toks.data_ptr()),
                                              c_void_p(lens.data_ptr())))
             return toks, lens
@@ -243,6 +266,7 @@ class Whisper:
             n = pcm.shape[0]
             toks = torch.empty((n, c.max_tokens), dtype=torch.int32, device=pcm.device)
             lens = torch.empty((n,), dtype=torch.int32, device=pcm.device)
+            self._order_after_torch(pcm.device)
             _lib.check(lib.wm_transcribe_pcm_dev(self._h, c_void_p(pcm.data_ptr()), n, c_void_p(toks.data_ptr()),
                                                  c_void_p(lens.data_ptr())))
             return toks, lens
@@ -275,6 +299,7 @@ class Whisper:
         """enc_out [n, ctx, d] (CUDA torch tensor) and forced int32 [n, n_forced] -> logits
         [n, n_forced - 3, vocab] with the greedy loop's position rule (parity tests)."""
         assert _is_cuda_tensor(enc_out)
+        self._order_after_torch(enc_out.device)
         f = np.ascontiguousarray(forced, np.int32)
         n, nf = f.shape
         out = np.empty((n, nf - 3, self.config.vocab_size), np.float32)

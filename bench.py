@@ -332,9 +332,9 @@ def parity_checks(args, model, cfg, toks_all, lens_all, n_total, dev, seed):
             bad = np.nonzero(got[:n] != ref[:n])[0]
             first = int(bad[0]) if len(bad) else None
             rows.append({"chunk": i, "ids": int(len(ref)), "matched": int(first if first is not None else n),
-                         "identical": first is None and len(got) == len(ref),
+                         "identical": bool(first is None and len(got) == len(ref)),
                          "oracle_margin_at_first_mismatch": None if first is None else float(mg[first - 4]),
-                         "ok": (first is None and len(got) == len(ref)) or (first is not None and first >= 4 and mg[first - 4] < 2e-2)})
+                         "ok": bool((first is None and len(got) == len(ref)) or (first is not None and first >= 4 and mg[first - 4] < 2e-2))})
         out["oracle"] = {"rule": "ids identical to the fp32 oracle, or first mismatch where the oracle top-1/top-2 margin < 2e-2",
                          "chunks": rows, "ok": all(r["ok"] for r in rows), "identical": sum(r["identical"] for r in rows)}
     except Exception as ex:
@@ -593,7 +593,10 @@ def run_b200(args):
             "cpu_baseline": cpu, "cpu_baseline_hf_generate": cpu_hf, "bf16_variant": bf16_line, "decode_breakdown": breakdown,
             "phases_ms_per_step": phases, "device_ms_each_step": step_ms, "decode_ms_each_step": step_decode_ms,
         }
-        print(json.dumps(line), file=json_out, flush=True)
+        def plain(o):  # numpy scalars that slipped into the record
+            return o.item() if hasattr(o, "item") else str(o)
+
+        print(json.dumps(line, default=plain), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

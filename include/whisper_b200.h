@@ -147,7 +147,8 @@ int wm_weight_tensor(wm_model m, int index, void **dev_ptr, int64_t *n_floats);
  * cross-attention launches, 2 = every decode kernel by category), "pdl" (programmatic dependent launch, default 0), "small_batch" (waves of at most this many chunks use the
  * latency-oriented decode: K/V-form cross-attention split over the SMs + programmatic dependent launch; default 0 = off,
  * 8 is a good value for batch-1 use), "decode_split_k" (split-K residual GEMMs + fused residual/LayerNorm in
- * the decode step: 0 = off, 1 = for batches >= 512 (default), 2 = always). */
+ * the decode step: 0 = off, 1 = on (default); never a function of the batch size, so a chunk's ids do not depend
+ * on how many chunks share its wave). */
 int wm_set_option(wm_model m, const char *key, int64_t value);
 
 /* Log-mel frontend (HF WhisperFeatureExtractor via export_weights.py:116): pcm f32 [n_chunks,

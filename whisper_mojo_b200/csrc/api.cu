@@ -432,7 +432,7 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
     else if (!strcmp(key, "attn_impl")) m->attn_impl = (int)value;
     else if (!strcmp(key, "frontend_impl")) m->frontend_impl = (int)value;
     else if (!strcmp(key, "decode_split_k")) {
-        WB_ARG(value >= 0 && value <= 2, "decode_split_k: 0 = off, 1 = for batches >= 512 (default), 2 = always");
+        WB_ARG(value >= 0 && value <= 2, "decode_split_k: 0 = off, 1 / 2 = on (default; independent of the batch size)");
         m->decode_split_k = (int)value;
         if (m->tr_cache) {  // the captured decode graph holds the old kernel sequence
             cache_destroy(m->tr_cache);

@@ -503,7 +503,9 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     auto resid_gemm_ln = [&](int cat, const h16 *A, int K, const h16 *Wt, const float *bias, const float *g,
                              const float *bb) -> int {
         int split = 1;
-        if (impl == GEMM_IMPL_TC && ln.part && (m->decode_split_k == 2 || (m->decode_split_k == 1 && B >= 512)))
+        // the split is a property of the model, never of the batch size: a chunk's fp32 sums (hence its ids at
+        // low-margin steps) must not depend on how many other chunks share the wave (bench parity.cross_g)
+        if (impl == GEMM_IMPL_TC && ln.part && m->decode_split_k >= 1)
             for (int sp : {4, 3, 2})
                 if (K % (64 * sp) == 0 && K / sp >= 192) {
                     split = sp;

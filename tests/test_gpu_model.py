@@ -561,3 +561,39 @@ def test_pageable_and_pinned_host_buffers_give_the_same_ids():
     assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
     td, ld = m.transcribe_pcm_batch(torch.from_numpy(a).cuda())
     assert np.array_equal(td.cpu().numpy(), t0)
+
+
+def test_kernel_per_op_decode_path_still_matches_oracle(setup):
+    """decode_fused = 0 keeps round 1's decode step (one kernel per op, 12 L + 4 launches); the default is the
+    persistent chain kernels of decode_chain.cu (4 L + 3 launches).  Both must meet the oracle bounds; they differ in
+    the split-K factors of the residual GEMMs, so logits agree to rounding, not bit for bit."""
+    cfg, mel, m, om, enc_ref = setup
+    m0, _ = build(cfg, decode_fused=0)
+    t0, l0 = m0.transcribe_batch(mel)
+    refs, mgs = [], []
+    for i in range(len(mel)):
+        r, mg = om.greedy(enc_ref[i], margins=True)
+        refs.append(r), mgs.append(mg)
+    ok, ident, text = token_report([t0[i, :l0[i]] for i in range(len(mel))], refs, mgs, MARGIN_TAU)
+    assert ok, text
+    forced = np.stack([np.concatenate([np.array(cfg.prompt), np.random.default_rng(50 + i).integers(0, cfg.vocab_size, 8)])
+                       for i in range(len(mel))]).astype(np.int32)
+    enc = torch.from_numpy(enc_ref).cuda()
+    la, lb = m.teacher_forced(enc, forced), m0.teacher_forced(enc, forced)
+    ref = np.stack([om.teacher_forced(enc_ref[i], forced[i]) for i in range(len(mel))])
+    assert np.abs(la - ref).max() <= LOGIT_MAX and np.abs(lb - ref).max() <= LOGIT_MAX
+    assert np.abs(la - lb).max() <= LOGIT_MAX
+
+
+def test_fused_decode_ragged_batches_are_batch_invariant():
+    """The chain kernels tile the batch in 128-row tiles and 16-row units: 1, 17, 129 and 300 chunks exercise ragged
+    last tiles / units and more than one row tile; a chunk's ids must be the same in all of them, run after run."""
+    cfg = WhisperConfig.micro()
+    m, _ = build(cfg)
+    mel = synth.make_mel(300, cfg, 17)
+    t300, l300 = m.transcribe_batch(mel)
+    for n in (1, 17, 129):
+        t, l = m.transcribe_batch(mel[:n])
+        assert np.array_equal(t, t300[:n]) and np.array_equal(l, l300[:n]), n
+    t2, _ = m.transcribe_batch(mel)
+    assert np.array_equal(t2, t300)

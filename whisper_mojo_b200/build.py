@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libwhisper_b200.so")  # fp16 operands (default; csrc/dtype.h)
 LIB_BF16 = os.path.join(HERE, "libwhisper_b200_bf16.so")  # -DWB_BF16: the bf16 variant, for A/B numbers
-SOURCES = ["api.cu", "ops.cu", "gemm.cu", "kernels.cu", "frontend.cu", "frontend_tc.cu", "model.cu", "attn_tc.cu", "cross_attn_tc.cu"]
+SOURCES = ["api.cu", "ops.cu", "gemm.cu", "kernels.cu", "frontend.cu", "frontend_tc.cu", "model.cu", "attn_tc.cu", "cross_attn_tc.cu", "decode_chain.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
               "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -446,6 +446,14 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
             m->tr_cache = nullptr;
         }
     }
+    else if (!strcmp(key, "decode_fused")) {
+        WB_ARG(value == 0 || value == 1, "decode_fused must be 0 or 1");
+        if (m->decode_fused != (int)value && m->tr_cache) {
+            cache_destroy(m->tr_cache);
+            m->tr_cache = nullptr;
+        }
+        m->decode_fused = (int)value;
+    }
     else if (!strcmp(key, "use_graph")) m->use_graph = (int)value;
     else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
     else if (!strcmp(key, "cross_impl")) {
@@ -664,7 +672,8 @@ int wm_last_timing(wm_model h, float ms[5]) {
 int wm_last_kernel_timing(wm_model h, const char *kernel, float *total_ms, int64_t *launches) {
     MODEL(m, h);
     static const char *names[TK_COUNT] = {"cross_attention", "self_attention", "gemm_qkv", "gemm_o", "gemm_cross_q",
-                                          "gemm_cross_o", "gemm_fc1", "gemm_fc2", "layer_norm", "gemm_logits", "misc"};
+                                          "gemm_cross_o", "gemm_fc1", "gemm_fc2", "layer_norm", "gemm_logits", "misc",
+                                          "chain_first", "chain_b", "chain_ca"};
     WB_ARG(kernel, "null kernel name");
     for (int k = 0; k < TK_COUNT; k++)
         if (!strcmp(kernel, names[k])) {

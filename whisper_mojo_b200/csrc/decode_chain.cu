@@ -1,0 +1,428 @@
+// decode_chain.cu -- persistent phase-list kernel for the dense part of one decode step (see decode_chain.h).
+//
+// Grid: one CTA per SM (cooperative launch: every CTA is resident, which the inter-CTA arrival counters rely on).
+// Roles per CTA, as in gemm_tc_kernel: warp 0 = TMA producer (6-stage ring, 128-byte swizzle), warp 1 = tcgen05.mma
+// issuer (UMMA 128 x 128 x 16, fp32 accumulators double-buffered in TMEM), warps 2..9 = epilogue AND row phases.
+// Every role walks the phase list in order with its own loop; they meet only through the mbarrier pipeline.
+//
+// Dependencies.  Phase p consumes, for a row tile mt (128 chunks), what phase p-1 produced for the same rows.
+// counters[p][mt] counts arrivals of phase p's producers for that tile (8 epilogue warps per GEMM tile; 8 warps per
+// 16-row unit of a row phase).  Consumers poll with ld.acquire.gpu; producers store, fence (gpu scope + the
+// generic->async proxy fence, since the next reader is a TMA load), then red.release.gpu.  Tiles are walked row-tile
+// major in every phase, so row tile 0 of phase p+1 starts while the later row tiles of phase p are still running.
+// No cycles: a wait only ever points at an EARLIER phase, and every role finishes its phase-p work before p+1.
+#include "decode_chain.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "gemm_dev.cuh"
+
+namespace wb {
+
+int make_tmap_h16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                  uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
+
+enum { PH_GEMM = 0, PH_ROWS = 1 };
+static constexpr int UNIT_ROWS = 16;  // rows per unit of a row phase: 2 per epilogue warp
+
+struct ChainPhase {
+    CUtensorMap a_map;  // A [M][K], box {64, 128}
+    CUtensorMap b_map;  // W [N][K], box {64, 128}
+    GemmDev d;          // rows_per_batch = M, batches = split_k ("batch" b = K slice), num_kb per slice
+    int type, tiles_n, splits;
+    // row phase
+    float *x;
+    const float *part;
+    int n_split;
+    const float *rbias, *gamma, *beta;
+    h16 *xn;
+    int embed;
+    const float *tok_emb, *pos_emb;
+    const int *cur_tok, *pos_dev;
+    int vocab, n_pos;
+};
+
+struct ChainParams {
+    int n_phases, M, D, tiles_m;
+    int *counters;  // [CHAIN_MAX_PHASES][tiles_m]
+    ChainPhase ph[CHAIN_MAX_PHASES];
+};
+
+struct ChainPlan {
+    ChainParams P;
+    int grid = 1;
+};
+
+__device__ __forceinline__ void chain_wait(const int *ctr, int target) {
+    uint64_t t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) return;
+        if ((spins & 0x3ffu) == 0) {  // bounded: a protocol bug traps instead of hanging the GPU
+            uint64_t t = ptx::globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 10000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void chain_signal(int *ctr) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ctr), "r"(1) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// arrivals that complete row tile `mt` of phase `q`
+__device__ __forceinline__ int chain_target(const ChainParams &P, int q, int mt) {
+    const ChainPhase &ph = P.ph[q];
+    if (ph.type == PH_GEMM) return ph.tiles_n * ph.splits * 8;
+    const int rows = min(BM, P.M - mt * BM);
+    return ((rows + UNIT_ROWS - 1) / UNIT_ROWS) * 8;
+}
+
+// One row of a row phase, one warp (D % 128 == 0, D <= 1024): see ChainRows.
+__device__ __forceinline__ void chain_row(const ChainPhase &ph, int row, int M, int D, int lane) {
+    float4 v[8];
+    const int nvec = D >> 7;
+    if (ph.embed) {
+        int tok = ph.cur_tok[row];
+        tok = tok < 0 ? 0 : (tok >= ph.vocab ? ph.vocab - 1 : tok);
+        int pos = *ph.pos_dev;
+        pos = pos < 0 ? 0 : (pos >= ph.n_pos ? ph.n_pos - 1 : pos);
+        const float4 *te = reinterpret_cast<const float4 *>(ph.tok_emb + (size_t)tok * D);
+        const float4 *pe = reinterpret_cast<const float4 *>(ph.pos_emb + (size_t)pos * D);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < nvec) {
+                const float4 a = te[i * 32 + lane], b = pe[i * 32 + lane];
+                v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+                reinterpret_cast<float4 *>(ph.x + (size_t)row * D)[i * 32 + lane] = v[i];
+            }
+    } else {
+        float4 *xr = reinterpret_cast<float4 *>(ph.x + (size_t)row * D);
+        const long long split_stride = (long long)M * D;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < nvec) {
+                float4 a = xr[i * 32 + lane];
+                if (ph.rbias) {
+                    const float4 b = reinterpret_cast<const float4 *>(ph.rbias)[i * 32 + lane];
+                    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+                }
+                for (int s = 0; s < ph.n_split; s++) {  // fixed order: deterministic, batch independent
+                    // written by other CTAs of this launch: plain (coherent) loads, never the read-only path
+                    // (ld.global.cg: the buffer is rewritten by a later phase of the same launch, so a stale L1 line
+                    // from an earlier read of these addresses on this SM must not be hit)
+                    const float4 pp = __ldcg(reinterpret_cast<const float4 *>(ph.part + (size_t)s * split_stride + (size_t)row * D) + i * 32 + lane);
+                    a.x += pp.x, a.y += pp.y, a.z += pp.z, a.w += pp.w;
+                }
+                v[i] = a;
+                xr[i * 32 + lane] = a;
+            }
+    }
+    if (!ph.gamma) return;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < nvec) {
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+            q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    const float mean = s / (float)D;  // one-pass variance, whisper_tensor.mojo:249-285
+    const float var = q / (float)D - mean * mean;
+    const float inv_std = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < nvec) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(ph.gamma) + i * 32 + lane);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(ph.beta) + i * 32 + lane);
+            uint2 pk;
+            pk.x = pack_h2((v[i].x - mean) * inv_std * g.x + b.x, (v[i].y - mean) * inv_std * g.y + b.y);
+            pk.y = pack_h2((v[i].z - mean) * inv_std * g.z + b.z, (v[i].w - mean) * inv_std * g.w + b.w);
+            reinterpret_cast<uint2 *>(ph.xn + (size_t)row * D)[i * 32 + lane] = pk;
+        }
+}
+
+template <int EPI>
+__device__ __forceinline__ void chain_epilogue(const GemmDev &p, int b, int m, int n_first, const uint32_t *v0,
+                                               const uint32_t *v1, const float *sbias) {
+    // (the accumulator is already in registers; global loads this needs are none for the three epilogues used here)
+    EpiChunk<EPI> e0, e1;
+    epi_prefetch<EPI>(p, b, m, n_first, e0);
+    epi_prefetch<EPI>(p, b, m, n_first + 32, e1);
+    float best = 0.f;
+    int best_idx = 0;
+    epi_finish<EPI>(p, b, m, n_first, v0, e0, sbias, best, best_idx);
+    epi_finish<EPI>(p, b, m, n_first + 32, v1, e1, sbias + 32, best, best_idx);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = tiles;
+    uint8_t *smem_b = tiles + STAGES * A_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint64_t *full_bar = bars, *empty_bar = bars + STAGES;
+    uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    float *bias_smem = reinterpret_cast<float *>(tiles + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256);  // [8][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = (int)gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        for (int p = 0; p < P.n_phases; p++)
+            if (P.ph[p].type == PH_GEMM) {
+                ptx::prefetch_tmap(&P.ph[p].a_map);
+                ptx::prefetch_tmap(&P.ph[p].b_map);
+            }
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], 8);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_holder, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int p = 0; p < P.n_phases; p++) {
+                const ChainPhase &ph = P.ph[p];
+                if (ph.type != PH_GEMM) continue;
+                const int per_mt = ph.tiles_n * ph.splits, total = P.tiles_m * per_mt, nkb = ph.d.num_kb;
+                for (int t = blockIdx.x; t < total; t += G) {
+                    const int mt = t / per_mt, r = t - mt * per_mt, sp = r / ph.tiles_n, nt = r - sp * ph.tiles_n;
+                    const int koff = sp * ph.d.split_koff;
+                    bool ready = (p == 0);
+                    for (int kb0 = 0; kb0 < nkb; kb0 += STAGES) {
+                        const int n = min(STAGES, nkb - kb0);
+                        // weights first: they depend on nothing, so they stream while the previous phase finishes
+                        int s = stage;
+                        uint32_t phs = phase;
+                        for (int i = 0; i < n; i++) {
+                            ptx::mbar_wait(&empty_bar[s], phs ^ 1);
+                            ptx::mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+                            ptx::tma_load_2d(smem_b + s * B_STAGE_BYTES, &ph.b_map, &full_bar[s], (kb0 + i) * BK + koff, nt * BN);
+                            if (++s == STAGES) s = 0, phs ^= 1;
+                        }
+                        if (!ready) {  // the activations of this row tile: produced by phase p-1 of this launch
+                            chain_wait(P.counters + (p - 1) * P.tiles_m + mt, chain_target(P, p - 1, mt));
+                            fence_proxy_async_all();
+                            ready = true;
+                        }
+                        s = stage;
+                        for (int i = 0; i < n; i++) {
+                            ptx::tma_load_2d(smem_a + s * A_STAGE_BYTES, &ph.a_map, &full_bar[s], (kb0 + i) * BK + koff, mt * BM);
+                            if (++s == STAGES) s = 0;
+                        }
+                        stage = s, phase = phs;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_h16(BM, BN, 0, 0);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int p = 0; p < P.n_phases; p++) {
+                const ChainPhase &ph = P.ph[p];
+                if (ph.type != PH_GEMM) continue;
+                const int total = P.tiles_m * ph.tiles_n * ph.splits, nkb = ph.d.num_kb;
+                for (int t = blockIdx.x; t < total; t += G, it++) {
+                    const int acc = it & 1;
+                    ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kb = 0; kb < nkb; kb++) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES), 1, 64);
+                        const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES), 1, 64);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)
+                            ptx::mma_h16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        ptx::mma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) stage = 0, phase ^= 1;
+                    }
+                    ptx::mma_commit(&tmem_full[acc]);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps (TMEM lanes 32 * (warp % 4) .. +31, columns 64 * half .. +63) and row phases =====
+        const int q = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+        float *sbias = bias_smem + ew * 128;
+        int it = 0;
+        for (int p = 0; p < P.n_phases; p++) {
+            const ChainPhase &ph = P.ph[p];
+            int *ctr = P.counters + p * P.tiles_m;
+            const bool signal = p + 1 < P.n_phases;  // the last phase is followed by the kernel boundary
+            if (ph.type == PH_GEMM) {
+                const GemmDev &d = ph.d;
+                const int per_mt = ph.tiles_n * ph.splits, total = P.tiles_m * per_mt;
+                for (int t = blockIdx.x; t < total; t += G, it++) {
+                    const int mt = t / per_mt, r = t - mt * per_mt, sp = r / ph.tiles_n, nt = r - sp * ph.tiles_n;
+                    const int acc = it & 1;
+                    const int m = mt * BM + q * 32 + lane;
+                    ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+                    ptx::tc_fence_after();
+                    const int n_first = nt * BN + half * 64;
+                    uint32_t v0[32], v1[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * 64;
+                    ptx::tmem_ld_32x32b_x32(taddr, v0);
+                    ptx::tmem_ld_32x32b_x32(taddr + 32, v1);
+                    stage_bias(d, n_first, 64, sbias, lane);
+                    ptx::tmem_ld_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_relaxed(&tmem_empty[acc]);  // accumulator is in registers
+                    switch (d.epi) {
+                        case EPI_GELU_H16: chain_epilogue<EPI_GELU_H16>(d, sp, m, n_first, v0, v1, sbias); break;
+                        case EPI_STORE_F32: chain_epilogue<EPI_STORE_F32>(d, sp, m, n_first, v0, v1, sbias); break;
+                        default: chain_epilogue<EPI_STORE_H16>(d, sp, m, n_first, v0, v1, sbias); break;
+                    }
+                    if (signal) {
+                        __threadfence();
+                        fence_proxy_async_all();
+                        __syncwarp();
+                        if (lane == 0) chain_signal(ctr + mt);
+                    }
+                }
+            } else {
+                const int n_units = (P.M + UNIT_ROWS - 1) / UNIT_ROWS;
+                for (int u = blockIdx.x; u < n_units; u += G) {
+                    const int mt = (u * UNIT_ROWS) / BM;
+                    if (p > 0) {
+                        if (lane == 0) chain_wait(P.counters + (p - 1) * P.tiles_m + mt, chain_target(P, p - 1, mt));
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < UNIT_ROWS / 8; rr++) {
+                        const int row = u * UNIT_ROWS + ew * (UNIT_ROWS / 8) + rr;
+                        if (row < P.M) chain_row(ph, row, P.M, P.D, lane);
+                    }
+                    if (signal) {
+                        __threadfence();
+                        fence_proxy_async_all();
+                        __syncwarp();
+                        if (lane == 0) chain_signal(ctr + mt);
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+size_t chain_counter_ints(int M) { return (size_t)CHAIN_MAX_PHASES * cdiv(M, BM); }
+
+int chain_split_k(int K) {
+    // ~12 k-blocks of 64 per tile (the ring is 6 deep: two refills), and the slices must tile K exactly
+    const int kb = K / BK;
+    int s = std::max(1, (kb + 11) / 12);
+    while (kb % s) s++;
+    return s;
+}
+
+ChainPlan *chain_plan_create(int M, int D, int *counters) {
+    ChainPlan *p = new ChainPlan();
+    p->P.n_phases = 0, p->P.M = M, p->P.D = D, p->P.tiles_m = cdiv(M, BM), p->P.counters = counters;
+    return p;
+}
+void chain_plan_destroy(ChainPlan *p) { delete p; }
+int chain_plan_phases(const ChainPlan *p) { return p->P.n_phases; }
+
+int chain_plan_add_gemm(ChainPlan *pl, const ChainGemm &g) {
+    ChainParams &P = pl->P;
+    WB_ARG(P.n_phases < CHAIN_MAX_PHASES, "chain: too many phases");
+    WB_ARG(g.A && g.W && g.K > 0 && g.K % BK == 0 && g.N > 0 && g.split_k >= 1 && (g.K / BK) % g.split_k == 0,
+           "chain: bad GEMM phase (K=%d N=%d split=%d)", g.K, g.N, g.split_k);
+    WB_ARG(g.epi == EPI_STORE_H16 || g.epi == EPI_GELU_H16 || g.epi == EPI_STORE_F32, "chain: unsupported epilogue %d", g.epi);
+    WB_ARG(g.split_k == 1 || (g.epi == EPI_STORE_F32 && !g.bias && g.n_seg_ptrs == 1 && !g.dyn_off),
+           "chain: split-K needs a plain bias-free fp32 partial output");
+    ChainPhase &ph = P.ph[P.n_phases];
+    memset(&ph, 0, sizeof ph);
+    ph.type = PH_GEMM;
+    ph.tiles_n = cdiv(g.N, BN);
+    ph.splits = g.split_k;
+    WB_CHECK(make_tmap_h16(&ph.a_map, g.A, (uint64_t)g.K, (uint64_t)P.M, 1, (uint64_t)g.K, 0, BM, 2));
+    WB_CHECK(make_tmap_h16(&ph.b_map, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.K, 0, BN, 2));
+    GemmDev &d = ph.d;
+    d.rows_per_batch = P.M, d.batches = g.split_k, d.N = g.N, d.K = g.K;
+    d.tiles_m_per_batch = P.tiles_m, d.tiles_n = ph.tiles_n;
+    d.split_koff = g.K / g.split_k;
+    d.num_kb = d.split_koff / BK, d.kb_per_tap = d.num_kb, d.taps = 1;
+    d.bias = g.bias, d.epi = g.epi;
+    for (int i = 0; i < 3; i++) d.out[i] = g.out[i], d.out_ld[i] = g.out_ld[i], d.dyn_mult[i] = g.dyn_mult[i];
+    d.seg_cols = g.seg_cols > 0 ? g.seg_cols : g.N;
+    d.n_seg_ptrs = g.n_seg_ptrs;
+    d.dyn_off = g.dyn_off;
+    WB_ARG(d.out[0] && (d.seg_cols == g.N || d.seg_cols % 32 == 0), "chain: bad output routing");
+    P.n_phases++;
+    pl->grid = std::max(pl->grid, P.tiles_m * ph.tiles_n * ph.splits);
+    return WB_OK;
+}
+
+int chain_plan_add_rows(ChainPlan *pl, const ChainRows &r) {
+    ChainParams &P = pl->P;
+    WB_ARG(P.n_phases < CHAIN_MAX_PHASES, "chain: too many phases");
+    WB_ARG(P.D % 128 == 0 && P.D <= 1024, "chain: D=%d must be a multiple of 128 and <= 1024", P.D);
+    WB_ARG(r.x && (!r.gamma || (r.beta && r.xn)) && (r.embed ? (r.tok_emb && r.pos_emb && r.cur_tok && r.pos_dev) : (r.n_split == 0 || r.part)),
+           "chain: bad row phase");
+    ChainPhase &ph = P.ph[P.n_phases];
+    memset(&ph, 0, sizeof ph);
+    ph.type = PH_ROWS;
+    ph.x = r.x, ph.part = r.part, ph.n_split = r.n_split, ph.rbias = r.bias, ph.gamma = r.gamma, ph.beta = r.beta, ph.xn = r.xn;
+    ph.embed = r.embed ? 1 : 0;
+    ph.tok_emb = r.tok_emb, ph.pos_emb = r.pos_emb, ph.cur_tok = r.cur_tok, ph.pos_dev = r.pos_dev;
+    ph.vocab = r.vocab, ph.n_pos = r.n_pos;
+    P.n_phases++;
+    pl->grid = std::max(pl->grid, cdiv(P.M, UNIT_ROWS));
+    return WB_OK;
+}
+
+int chain_launch(cudaStream_t st, const ChainPlan *pl) {
+    WB_ARG(pl && pl->P.n_phases > 0, "chain: empty plan");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    WB_CUDA(ensure_dyn_smem(decode_chain_kernel, TC_SMEM_BYTES));
+    // Cooperative launch: the whole grid is resident at once (one CTA per SM), which the arrival counters need --
+    // also when another stream's kernels compete for the SMs.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(std::min(pl->grid, sms)), cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    WB_CUDA(cudaLaunchKernelEx(&cfg, decode_chain_kernel, pl->P));
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+}  // namespace wb

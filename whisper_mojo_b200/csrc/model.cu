@@ -393,7 +393,11 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
         A(&ln.part_idx, (size_t)ln.B * slots);
         A(&ln.next, ln.B);
         A(&ln.attn_ws, (size_t)ln.B * ln.cross_splits * m->H * 66);
-        A(&ln.part, (size_t)4 * ln.B * D);  // split-K partial products of the residual GEMMs
+        // split-K partial products of the residual GEMMs: round 1's form uses up to 4 slices, the chain kernel
+        // chain_split_k(K) of them for K = D (o), H*D or D (cross-o) and F (fc2)
+        ln.part_splits = std::max({4, chain_split_k((int)D), chain_split_k(c->cross_impl == 1 ? m->H * (int)D : (int)D),
+                                   chain_split_k(m->F)});
+        A(&ln.part, (size_t)ln.part_splits * ln.B * D);
         if (c->cross_impl == 1) {
             A(&ln.qp, (size_t)ln.B * m->H * D);
             A(&ln.ctx, (size_t)ln.B * m->H * D);
@@ -405,6 +409,8 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
         ln.g.done = c->done + ln.b_off;
         ln.g.scalars = c->scalars + 4 * i;
         ln.g.T_out = T_out, ln.g.eot = m->cfg.eot, ln.g.pos_quirk = m->cfg.pos_quirk;
+        ln.counter_bytes = (size_t)(2 * m->L + 2) * chain_counter_ints(ln.B) * sizeof(int);
+        A(&ln.counters, ln.counter_bytes / sizeof(int));
     }
     if (ok && (cudaMallocHost((void **)&c->pinned_scalars, 16 * sizeof(int)) != cudaSuccess ||
                cudaEventCreateWithFlags(&c->poll_ev[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -427,6 +433,10 @@ void cache_destroy(Cache *c) {
         cudaStreamSynchronize(c->m->stream2);
     }
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (Lane &ln : c->lanes) {
+        for (ChainPlan *p : ln.plans) chain_plan_destroy(p);
+        chain_plan_destroy(ln.plan_last_nolog);
+    }
     for (void *p : c->owned) cudaFree(p);
     if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
     for (cudaEvent_t e : c->poll_ev)
@@ -463,6 +473,96 @@ int cache_set_encoder(Cache *c, const float *enc_out_dev) {
     return WB_OK;
 }
 
+// The fused decode step: one ChainPlan per kernel (decode_chain.h).  Buffers and weights are fixed for the life of
+// the cache, so the tensor maps and phase lists are built once here and the step only launches them.
+static int build_chain_plans(Cache *c, Lane &ln) {
+    Model *m = c->m;
+    WB_ARG(m->loaded, "decode before weights are loaded");
+    const int B = ln.B, D = m->D, L = m->L, F = m->F, HD = m->H * D;
+    const float *W = m->w32;
+    int *cur_len = ln.g.scalars, *pos = ln.g.scalars + 1;
+    const size_t self_seg = (size_t)c->B * c->T * D, self_off = (size_t)ln.b_off * c->T * D;
+    const size_t cstride = chain_counter_ints(B);
+    auto qkv_phase = [&](ChainPlan *p, int l) {
+        const LayerDev &d = m->dec[l];
+        h16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
+        ChainGemm g;  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
+        g.A = ln.xn, g.K = D, g.W = d.wqkv, g.N = 3 * D, g.bias = d.bqkv, g.epi = EPI_STORE_H16;
+        g.n_seg_ptrs = 3, g.seg_cols = D;
+        g.out[0] = ln.q, g.out_ld[0] = D;
+        g.out[1] = sk, g.out_ld[1] = (int64_t)c->T * D, g.dyn_mult[1] = D;
+        g.out[2] = sv, g.out_ld[2] = (int64_t)c->T * D, g.dyn_mult[2] = D;
+        g.dyn_off = cur_len;
+        return chain_plan_add_gemm(p, g);
+    };
+    auto partial_phase = [&](ChainPlan *p, const h16 *A, int K, const h16 *Wt) {
+        ChainGemm g;  // residual GEMM as split-K partial products; the row phase that follows adds them to x
+        g.A = A, g.K = K, g.W = Wt, g.N = D, g.epi = EPI_STORE_F32, g.split_k = chain_split_k(K);
+        g.out[0] = ln.part, g.out_ld[0] = D;
+        return chain_plan_add_gemm(p, g);
+    };
+    auto ln_phase = [&](ChainPlan *p, int K, const float *bias, const float *g, const float *b) {
+        ChainRows r;
+        r.x = ln.x, r.part = ln.part, r.n_split = chain_split_k(K), r.bias = bias, r.gamma = g, r.beta = b, r.xn = ln.xn;
+        return chain_plan_add_rows(p, r);
+    };
+    int idx = 0;
+    auto new_plan = [&]() { return chain_plan_create(B, D, ln.counters + cstride * (idx++)); };
+    {  // embed + attn_ln of layer 0 + qkv_0 (whisper.mojo:138-149)
+        ChainPlan *p = new_plan();
+        ln.plans.push_back(p);
+        ChainRows r;
+        r.embed = true, r.x = ln.x, r.xn = ln.xn, r.gamma = m->dec[0].ln1_g, r.beta = m->dec[0].ln1_b;
+        r.tok_emb = W + m->lay.tok_emb, r.pos_emb = W + m->lay.dec_pos, r.cur_tok = ln.g.cur_tok, r.pos_dev = pos;
+        r.vocab = m->V, r.n_pos = m->T;
+        WB_CHECK(chain_plan_add_rows(p, r));
+        WB_CHECK(qkv_phase(p, 0));
+    }
+    for (int l = 0; l < L; l++) {
+        const LayerDev &d = m->dec[l];
+        {  // self-attention output projection + residual, cross_attn_ln, cross query projection (layers.mojo:455-470)
+            ChainPlan *p = new_plan();
+            ln.plans.push_back(p);
+            WB_CHECK(partial_phase(p, ln.attn, D, d.wo));
+            WB_CHECK(ln_phase(p, D, d.bo, d.ln2_g, d.ln2_b));
+            ChainGemm g;
+            g.A = ln.xn, g.K = D, g.epi = EPI_STORE_H16;
+            if (c->cross_impl == 1) g.W = d.wqk, g.N = HD, g.bias = d.bqk, g.out[0] = ln.qp, g.out_ld[0] = HD;
+            else g.W = d.cwq, g.N = D, g.bias = d.cbq, g.out[0] = ln.q, g.out_ld[0] = D;
+            WB_CHECK(chain_plan_add_gemm(p, g));
+        }
+        const bool last = l + 1 == L;
+        for (int variant = 0; variant < (last ? 2 : 1); variant++) {
+            // cross-attention output projection + residual, mlp_ln, MLP (layers.mojo:482-517), then the LayerNorm in
+            // front of what follows -- the next layer's attn_ln + qkv, or the decoder's ln_post before the logits
+            // (whisper.mojo:156-158), or nothing on a prompt step (variant 1)
+            ChainPlan *p = new_plan();
+            if (variant == 0) ln.plans.push_back(p);
+            else ln.plan_last_nolog = p;
+            if (c->cross_impl == 1) {
+                WB_CHECK(partial_phase(p, ln.ctx, HD, d.wov));
+                WB_CHECK(ln_phase(p, HD, d.bov, d.ln3_g, d.ln3_b));
+            } else {
+                WB_CHECK(partial_phase(p, ln.attn, D, d.cwo));
+                WB_CHECK(ln_phase(p, D, d.cbo, d.ln3_g, d.ln3_b));
+            }
+            ChainGemm g;
+            g.A = ln.xn, g.K = D, g.W = d.w1, g.N = F, g.bias = d.b1, g.epi = EPI_GELU_H16, g.out[0] = ln.h, g.out_ld[0] = F;
+            WB_CHECK(chain_plan_add_gemm(p, g));
+            WB_CHECK(partial_phase(p, ln.h, F, d.w2));
+            if (!last) {
+                WB_CHECK(ln_phase(p, F, d.b2, m->dec[l + 1].ln1_g, m->dec[l + 1].ln1_b));
+                WB_CHECK(qkv_phase(p, l + 1));
+            } else if (variant == 0) {
+                WB_CHECK(ln_phase(p, F, d.b2, W + m->lay.dec_ln_w, W + m->lay.dec_ln_b));
+            } else {
+                WB_CHECK(ln_phase(p, F, d.b2, nullptr, nullptr));
+            }
+        }
+    }
+    return WB_OK;
+}
+
 template <typename Fn>
 static int timed_kernel(Model *m, cudaStream_t st, int category, Fn launch) {
     if (!(m->profile_attn == 2 || (m->profile_attn == 1 && category == TK_CROSS))) return launch();
@@ -491,6 +591,34 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     // cache-wide segment sizes; this lane's chunks start b_off rows into every segment
     const size_t self_seg = (size_t)c->B * c->T * D, cross_seg = (size_t)c->B * m->S * D;
     const size_t self_off = (size_t)ln.b_off * c->T * D, cross_off = (size_t)ln.b_off * m->S * D;
+    const bool fused = m->decode_fused && impl == GEMM_IMPL_TC && c->lanes.size() == 1;
+    if (fused && ln.plans.empty()) WB_CHECK(build_chain_plans(c, ln));  // host-only work (tensor maps): capture safe
+    if (fused) {
+        // 4 L + 3 kernels: chain | self-attn | chain | cross-attn | chain | ... | logits+argmax | argmax reduce
+        WB_CUDA(cudaMemsetAsync(ln.counters, 0, ln.counter_bytes, st));  // arrival counters of this step's chains
+        WB_CHECK(timed_kernel(m, st, TK_CHAIN_FIRST, [&] { return chain_launch(st, ln.plans[0]); }));
+        for (int l = 0; l < m->L; l++) {
+            h16 *sk = c->self_kv + (size_t)(l * 2) * self_seg + self_off, *sv = sk + self_seg;
+            DecodeAttnArgs a;
+            a.q = ln.q, a.K = sk, a.V = sv, a.out = ln.attn, a.kv_batch_stride = (int64_t)c->T * D;
+            a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
+            a.splits = 1, a.ws = nullptr;
+            WB_CHECK(timed_kernel(m, st, TK_SELF, [&] { return decode_attention(st, a); }));
+            WB_CHECK(timed_kernel(m, st, TK_CHAIN_B, [&] { return chain_launch(st, ln.plans[1 + 2 * l]); }));
+            if (c->cross_impl == 1) {
+                const h16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
+                WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
+            } else {
+                a.q = ln.q, a.K = c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off, a.V = a.K + cross_seg;
+                a.kv_batch_stride = (int64_t)m->S * D;
+                a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
+                a.splits = ln.cross_splits, a.ws = ln.attn_ws;
+                WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return decode_attention(st, a); }));
+            }
+            const ChainPlan *ca = (l + 1 == m->L && !with_logits) ? ln.plan_last_nolog : ln.plans[2 + 2 * l];
+            WB_CHECK(timed_kernel(m, st, TK_CHAIN_CA, [&] { return chain_launch(st, ca); }));
+        }
+    } else {
     WB_CHECK(timed_kernel(m, st, TK_LN, [&] {
         return embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, ln.g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
                         m->dec[0].ln1_b, ln.x, ln.xn);
@@ -573,6 +701,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         const float *nb = last ? (with_logits ? W + m->lay.dec_ln_b : nullptr) : m->dec[l + 1].ln1_b;
         WB_CHECK(resid_gemm_ln(TK_FC2, ln.h, m->F, d.w2, d.b2, ng, nb));
     }
+    }  // !fused
     if (with_logits) {  // whisper.mojo:156-166 + argmax :198,219
         GemmDesc g = plain_gemm(ln.xn, B, D, m->tok_emb_h16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
         g.part_val = ln.part_val, g.part_idx = ln.part_idx;
@@ -626,7 +755,9 @@ static int greedy_loop(Cache *c) {
     if (graph && !c->graph_exec) {
         cudaGraph_t gr = nullptr;
         WB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = g_launches.load();
         int rc = step_all_lanes(c, true, 1, 0);
+        c->graph_kernels = (int)(g_launches.load() - l0);  // kernel nodes of one step (another thread's launches aside)
         cudaError_t e = cudaStreamEndCapture(st, &gr);
         if (rc != WB_OK) {
             if (gr) cudaGraphDestroy(gr);
@@ -656,7 +787,7 @@ static int greedy_loop(Cache *c) {
         }
         if (graph) {
             WB_CUDA(cudaGraphLaunch(c->graph_exec, st));
-            g_launches.fetch_add((12 * m->L + 4) * n_lanes, std::memory_order_relaxed);  // kernels replayed by the graph
+            g_launches.fetch_add(c->graph_kernels, std::memory_order_relaxed);  // kernels replayed by the graph
         } else {
             WB_CHECK(step_all_lanes(c, true, 1, 0));
         }

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/whisper_b200.h"
+#include "decode_chain.h"
 #include "kernels.h"
 
 namespace wb {
@@ -43,7 +44,8 @@ struct LayerDev {
 
 // Event pairs around individual decode-step launches (option "profile_attn": 1 = cross-attention only, the
 // bench's roofline pass; 2 = every kernel of the step, by category).
-enum TimedKernel { TK_CROSS = 0, TK_SELF, TK_QKV, TK_O, TK_CQ, TK_CO, TK_FC1, TK_FC2, TK_LN, TK_LOGITS, TK_MISC, TK_COUNT };
+enum TimedKernel { TK_CROSS = 0, TK_SELF, TK_QKV, TK_O, TK_CQ, TK_CO, TK_FC1, TK_FC2, TK_LN, TK_LOGITS, TK_MISC,
+                   TK_CHAIN_FIRST, TK_CHAIN_B, TK_CHAIN_CA, TK_COUNT };
 struct KernelTimer {
     std::vector<cudaEvent_t> ev;
     std::vector<int> cat;  // category of event pair i
@@ -64,6 +66,8 @@ struct Model {
     int gemm_impl = 1, attn_impl = 1, frontend_impl = 1,  // frontend: 0 = fp32 FMA DFT, 1 = TF32x3 tensor-core DFT
          use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048, small_batch = 0,
         decode_split_k = 1,  // split-K residual GEMMs + fused residual/LayerNorm in the decode step
+        decode_fused = 1,  // 1 = the dense work between two attention kernels runs as one persistent chain kernel
+                           // (decode_chain.cu: 4 L + 3 kernels per step instead of 12 L + 4); 0 = round 1's kernel per op
         decode_lanes = 1,  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
         cross_impl = 1;    // 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (D <= 384)
     Layout lay;
@@ -101,6 +105,14 @@ struct Lane {
     h16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *qp = nullptr, *ctx = nullptr;
     int *part_idx = nullptr, *next = nullptr;
     int cross_splits = 1;
+    int part_splits = 4;  // slices the split-K partial buffer `part` holds
+    // fused decode step (decode_chain.cu): plans[0] = embed + LN + qkv_0, plans[1 + 2 l] = o -> LN -> cross-q of
+    // layer l, plans[2 + 2 l] = cross-o -> LN -> fc1 -> fc2 -> LN -> qkv_{l+1}; plan_last_nolog = the last layer's
+    // chain without the final LayerNorm (prompt steps, whose logits nobody reads)
+    std::vector<ChainPlan *> plans;
+    ChainPlan *plan_last_nolog = nullptr;
+    int *counters = nullptr;
+    size_t counter_bytes = 0;
     GreedyState g;  // per-chunk arrays point into the cache-wide arrays at b_off; scalars are per lane
 };
 
@@ -119,6 +131,7 @@ struct Cache {
     int *pinned_scalars = nullptr;           // two snapshots of the lanes' step scalars (lagged EOT poll)
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaGraphExec_t graph_exec = nullptr;
+    int graph_kernels = 0;  // kernels one replay of graph_exec launches
 };
 
 int model_create(const wm_config *cfg, void *stream, Model **out);

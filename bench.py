@@ -501,9 +501,10 @@ def run_b200(args):
             torch.cuda.synchronize()
             breakdown = {"chunks": C, "decode_ms_eager": model.last_timing()["decode_ms"], "kernels": {}}
             for k in ("cross_attention", "self_attention", "gemm_qkv", "gemm_o", "gemm_cross_q", "gemm_cross_o", "gemm_fc1",
-                      "gemm_fc2", "layer_norm", "gemm_logits", "misc"):
+                      "gemm_fc2", "layer_norm", "gemm_logits", "misc", "chain_first", "chain_b", "chain_ca"):
                 t_ms, n_l = model.last_kernel_timing(k)
-                breakdown["kernels"][k] = {"ms": t_ms, "launches": n_l, "us_each": 1e3 * t_ms / max(n_l, 1)}
+                if n_l:
+                    breakdown["kernels"][k] = {"ms": t_ms, "launches": n_l, "us_each": 1e3 * t_ms / max(n_l, 1)}
             model.set_option("profile_attn", 0)
         except Exception as ex:
             breakdown = {"error": str(ex)}

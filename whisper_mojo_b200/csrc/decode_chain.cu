@@ -14,6 +14,8 @@
 #include "decode_chain.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,7 +27,7 @@ int make_tmap_h16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, 
                   uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
 
 enum { PH_GEMM = 0, PH_ROWS = 1 };
-static constexpr int UNIT_ROWS = 16;  // rows per unit of a row phase: 2 per epilogue warp
+static constexpr int UNIT_ROWS = 8;  // rows per unit of a row phase: one per epilogue warp
 
 struct ChainPhase {
     CUtensorMap a_map;  // A [M][K], box {64, 128}
@@ -47,6 +49,7 @@ struct ChainPhase {
 struct ChainParams {
     int n_phases, M, D, tiles_m;
     int *counters;  // [CHAIN_MAX_PHASES][tiles_m]
+    unsigned long long *dbg;  // development aid (WB_CHAIN_DBG): CTA 0's timestamps [phase][role][8]
     ChainPhase ph[CHAIN_MAX_PHASES];
 };
 
@@ -54,6 +57,11 @@ struct ChainPlan {
     ChainParams P;
     int grid = 1;
 };
+
+#define CH_STAMP(p, role, ev)                                                                          \
+    do {                                                                                               \
+        if (P.dbg && blockIdx.x == 0) P.dbg[((p)*3 + (role)) * 8 + (ev)] = ptx::globaltimer_ns();      \
+    } while (0)
 
 __device__ __forceinline__ void chain_wait(const int *ctr, int target) {
     uint64_t t0 = 0;
@@ -81,69 +89,117 @@ __device__ __forceinline__ int chain_target(const ChainParams &P, int q, int mt)
     return ((rows + UNIT_ROWS - 1) / UNIT_ROWS) * 8;
 }
 
-// One row of a row phase, one warp (D % 128 == 0, D <= 1024): see ChainRows.
-__device__ __forceinline__ void chain_row(const ChainPhase &ph, int row, int M, int D, int lane) {
-    float4 v[8];
-    const int nvec = D >> 7;
+// R rows of a row phase handled by one warp (D % 128 == 0, D <= 1024), all their loads in flight together: see
+// ChainRows.  g / b: this lane's slices of gamma / beta, loaded by the caller BEFORE it waited for the producers.
+// NV = D / 128 float4 per lane and row (compile time: the arrays must stay in registers).
+template <int R, int NV>
+__device__ __forceinline__ void chain_rows(const ChainPhase &ph, int row0, int M, int lane) {
+    constexpr int nvec = NV, D = NV * 128;
+    float4 v[R][NV];
+    float4 g[NV], b[NV];  // gamma / beta slices: constants, their loads are independent of everything below
+    if (ph.gamma) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            g[i] = __ldg(reinterpret_cast<const float4 *>(ph.gamma) + i * 32 + lane);
+            b[i] = __ldg(reinterpret_cast<const float4 *>(ph.beta) + i * 32 + lane);
+        }
+    }
     if (ph.embed) {
-        int tok = ph.cur_tok[row];
-        tok = tok < 0 ? 0 : (tok >= ph.vocab ? ph.vocab - 1 : tok);
         int pos = *ph.pos_dev;
         pos = pos < 0 ? 0 : (pos >= ph.n_pos ? ph.n_pos - 1 : pos);
-        const float4 *te = reinterpret_cast<const float4 *>(ph.tok_emb + (size_t)tok * D);
         const float4 *pe = reinterpret_cast<const float4 *>(ph.pos_emb + (size_t)pos * D);
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (i < nvec) {
-                const float4 a = te[i * 32 + lane], b = pe[i * 32 + lane];
-                v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-                reinterpret_cast<float4 *>(ph.x + (size_t)row * D)[i * 32 + lane] = v[i];
-            }
-    } else {
-        float4 *xr = reinterpret_cast<float4 *>(ph.x + (size_t)row * D);
-        const long long split_stride = (long long)M * D;
+        for (int r = 0; r < R; r++) {
+            if (row0 + r >= M) continue;
+            int tok = ph.cur_tok[row0 + r];
+            tok = tok < 0 ? 0 : (tok >= ph.vocab ? ph.vocab - 1 : tok);
+            const float4 *te = reinterpret_cast<const float4 *>(ph.tok_emb + (size_t)tok * D);
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (i < nvec) {
-                float4 a = xr[i * 32 + lane];
-                if (ph.rbias) {
-                    const float4 b = reinterpret_cast<const float4 *>(ph.rbias)[i * 32 + lane];
-                    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+            for (int i = 0; i < NV; i++)
+                if (i < nvec) {
+                    const float4 a = te[i * 32 + lane], c = pe[i * 32 + lane];
+                    v[r][i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+                    reinterpret_cast<float4 *>(ph.x + (size_t)(row0 + r) * D)[i * 32 + lane] = v[r][i];
                 }
-                for (int s = 0; s < ph.n_split; s++) {  // fixed order: deterministic, batch independent
-                    // written by other CTAs of this launch: plain (coherent) loads, never the read-only path
-                    // (ld.global.cg: the buffer is rewritten by a later phase of the same launch, so a stale L1 line
-                    // from an earlier read of these addresses on this SM must not be hit)
-                    const float4 pp = __ldcg(reinterpret_cast<const float4 *>(ph.part + (size_t)s * split_stride + (size_t)row * D) + i * 32 + lane);
-                    a.x += pp.x, a.y += pp.y, a.z += pp.z, a.w += pp.w;
+        }
+    } else {
+        const long long split_stride = (long long)M * D;
+        // every load of both rows is issued before the first use: one L2 round trip, not one per slice
+        float4 pp[R][NV];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+                if (i < nvec && row0 + r < M) v[r][i] = reinterpret_cast<const float4 *>(ph.x + (size_t)(row0 + r) * D)[i * 32 + lane];
+        for (int s = 0; s < ph.n_split; s++) {  // fixed order: deterministic, batch independent
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int i = 0; i < NV; i++)
+                    if (i < nvec && row0 + r < M)
+                        // written by other CTAs of this launch, and rewritten by a later phase of it: ld.global.cg, so
+                        // a stale L1 line from an earlier read of these addresses on this SM cannot be hit
+                        pp[r][i] = __ldcg(reinterpret_cast<const float4 *>(ph.part + (size_t)s * split_stride + (size_t)(row0 + r) * D) + i * 32 + lane);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int i = 0; i < NV; i++)
+                    if (i < nvec && row0 + r < M) {
+                        float4 a = v[r][i];
+                        if (s == 0 && ph.rbias) {  // x + bias first, then the slices in order (as resid_ln)
+                            const float4 c = __ldg(reinterpret_cast<const float4 *>(ph.rbias) + i * 32 + lane);
+                            a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
+                        }
+                        a.x += pp[r][i].x, a.y += pp[r][i].y, a.z += pp[r][i].z, a.w += pp[r][i].w;
+                        v[r][i] = a;
+                    }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+                if (i < nvec && row0 + r < M) {
+                    if (ph.n_split == 0 && ph.rbias) {
+                        const float4 c = __ldg(reinterpret_cast<const float4 *>(ph.rbias) + i * 32 + lane);
+                        v[r][i].x += c.x, v[r][i].y += c.y, v[r][i].z += c.z, v[r][i].w += c.w;
+                    }
+                    reinterpret_cast<float4 *>(ph.x + (size_t)(row0 + r) * D)[i * 32 + lane] = v[r][i];
                 }
-                v[i] = a;
-                xr[i * 32 + lane] = a;
-            }
     }
     if (!ph.gamma) return;
-    float s = 0.f, q = 0.f;
+    float s[R], q[R];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        if (i < nvec) {
-            s += v[i].x + v[i].y + v[i].z + v[i].w;
-            q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-        }
-    s = warp_sum(s);
-    q = warp_sum(q);
-    const float mean = s / (float)D;  // one-pass variance, whisper_tensor.mojo:249-285
-    const float var = q / (float)D - mean * mean;
-    const float inv_std = 1.0f / sqrtf(var + 1e-5f);
+    for (int r = 0; r < R; r++) {
+        s[r] = q[r] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        if (i < nvec) {
-            const float4 g = __ldg(reinterpret_cast<const float4 *>(ph.gamma) + i * 32 + lane);
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(ph.beta) + i * 32 + lane);
-            uint2 pk;
-            pk.x = pack_h2((v[i].x - mean) * inv_std * g.x + b.x, (v[i].y - mean) * inv_std * g.y + b.y);
-            pk.y = pack_h2((v[i].z - mean) * inv_std * g.z + b.z, (v[i].w - mean) * inv_std * g.w + b.w);
-            reinterpret_cast<uint2 *>(ph.xn + (size_t)row * D)[i * 32 + lane] = pk;
+        for (int i = 0; i < NV; i++)
+            if (i < nvec && row0 + r < M) {
+                s[r] += v[r][i].x + v[r][i].y + v[r][i].z + v[r][i].w;
+                q[r] += v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y + v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w;
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+            q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
         }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (row0 + r >= M) continue;
+        const float mean = s[r] / (float)D;  // one-pass variance, whisper_tensor.mojo:249-285
+        const float var = q[r] / (float)D - mean * mean;
+        const float inv_std = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < NV; i++)
+            if (i < nvec) {
+                uint2 pk;
+                pk.x = pack_h2((v[r][i].x - mean) * inv_std * g[i].x + b[i].x, (v[r][i].y - mean) * inv_std * g[i].y + b[i].y);
+                pk.y = pack_h2((v[r][i].z - mean) * inv_std * g[i].z + b[i].z, (v[r][i].w - mean) * inv_std * g[i].w + b[i].w);
+                reinterpret_cast<uint2 *>(ph.xn + (size_t)(row0 + r) * D)[i * 32 + lane] = pk;
+            }
+    }
 }
 
 template <int EPI>
@@ -159,6 +215,8 @@ __device__ __forceinline__ void chain_epilogue(const GemmDev &p, int b, int m, i
     epi_finish<EPI>(p, b, m, n_first + 32, v1, e1, sbias + 32, best, best_idx);
 }
 
+// NV = d_model / 128 (the row phases keep a row in registers).
+template <int NV>
 __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -211,6 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                     const int mt = t / per_mt, r = t - mt * per_mt, sp = r / ph.tiles_n, nt = r - sp * ph.tiles_n;
                     const int koff = sp * ph.d.split_koff;
                     bool ready = (p == 0);
+                    if (t == (int)blockIdx.x) CH_STAMP(p, 0, 0);
                     for (int kb0 = 0; kb0 < nkb; kb0 += STAGES) {
                         const int n = min(STAGES, nkb - kb0);
                         // weights first: they depend on nothing, so they stream while the previous phase finishes
@@ -222,17 +281,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                             ptx::tma_load_2d(smem_b + s * B_STAGE_BYTES, &ph.b_map, &full_bar[s], (kb0 + i) * BK + koff, nt * BN);
                             if (++s == STAGES) s = 0, phs ^= 1;
                         }
+                        if (t == (int)blockIdx.x && kb0 == 0) CH_STAMP(p, 0, 1);
                         if (!ready) {  // the activations of this row tile: produced by phase p-1 of this launch
                             chain_wait(P.counters + (p - 1) * P.tiles_m + mt, chain_target(P, p - 1, mt));
                             fence_proxy_async_all();
                             ready = true;
                         }
+                        if (t == (int)blockIdx.x && kb0 == 0) CH_STAMP(p, 0, 2);
                         s = stage;
                         for (int i = 0; i < n; i++) {
                             ptx::tma_load_2d(smem_a + s * A_STAGE_BYTES, &ph.a_map, &full_bar[s], (kb0 + i) * BK + koff, mt * BM);
                             if (++s == STAGES) s = 0;
                         }
                         stage = s, phase = phs;
+                        if (t == (int)blockIdx.x && kb0 == 0) CH_STAMP(p, 0, 3);
                     }
                 }
             }
@@ -254,6 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     for (int kb = 0; kb < nkb; kb++) {
                         ptx::mbar_wait(&full_bar[stage], phase);
+                        if (t == (int)blockIdx.x && kb == 0) CH_STAMP(p, 1, 0);
                         ptx::tc_fence_after();
                         const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES), 1, 64);
                         const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES), 1, 64);
@@ -264,6 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                         if (++stage == STAGES) stage = 0, phase ^= 1;
                     }
                     ptx::mma_commit(&tmem_full[acc]);
+                    if (t == (int)blockIdx.x) CH_STAMP(p, 1, 1);
                 }
             }
         }
@@ -283,14 +347,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                     const int mt = t / per_mt, r = t - mt * per_mt, sp = r / ph.tiles_n, nt = r - sp * ph.tiles_n;
                     const int acc = it & 1;
                     const int m = mt * BM + q * 32 + lane;
-                    ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-                    ptx::tc_fence_after();
                     const int n_first = nt * BN + half * 64;
+                    stage_bias(d, n_first, 64, sbias, lane);  // before the wait: its global loads overlap the MMAs
+                    ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+                    if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 0);
+                    ptx::tc_fence_after();
                     uint32_t v0[32], v1[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * 64;
                     ptx::tmem_ld_32x32b_x32(taddr, v0);
                     ptx::tmem_ld_32x32b_x32(taddr + 32, v1);
-                    stage_bias(d, n_first, 64, sbias, lane);
                     ptx::tmem_ld_wait();
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -300,12 +365,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                         case EPI_STORE_F32: chain_epilogue<EPI_STORE_F32>(d, sp, m, n_first, v0, v1, sbias); break;
                         default: chain_epilogue<EPI_STORE_H16>(d, sp, m, n_first, v0, v1, sbias); break;
                     }
+                    if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 1);
                     if (signal) {
-                        __threadfence();
+                        // every lane's stores -> (generic -> async proxy fence) -> warp barrier -> one releasing
+                        // reduction at gpu scope: the release is cumulative over the lanes the barrier ordered before it
                         fence_proxy_async_all();
                         __syncwarp();
                         if (lane == 0) chain_signal(ctr + mt);
                     }
+                    if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 2);
                 }
             } else {
                 const int n_units = (P.M + UNIT_ROWS - 1) / UNIT_ROWS;
@@ -315,17 +383,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                         if (lane == 0) chain_wait(P.counters + (p - 1) * P.tiles_m + mt, chain_target(P, p - 1, mt));
                         __syncwarp();
                     }
-#pragma unroll
-                    for (int rr = 0; rr < UNIT_ROWS / 8; rr++) {
-                        const int row = u * UNIT_ROWS + ew * (UNIT_ROWS / 8) + rr;
-                        if (row < P.M) chain_row(ph, row, P.M, P.D, lane);
-                    }
+                    if (u == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 0);
+                    const int row0 = u * UNIT_ROWS + ew * (UNIT_ROWS / 8);
+                    chain_rows<UNIT_ROWS / 8, NV>(ph, row0, P.M, lane);
+                    if (u == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 1);
                     if (signal) {
-                        __threadfence();
                         fence_proxy_async_all();
                         __syncwarp();
                         if (lane == 0) chain_signal(ctr + mt);
                     }
+                    if (u == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 2);
                 }
             }
         }
@@ -350,7 +417,7 @@ int chain_split_k(int K) {
 
 ChainPlan *chain_plan_create(int M, int D, int *counters) {
     ChainPlan *p = new ChainPlan();
-    p->P.n_phases = 0, p->P.M = M, p->P.D = D, p->P.tiles_m = cdiv(M, BM), p->P.counters = counters;
+    p->P.n_phases = 0, p->P.M = M, p->P.D = D, p->P.tiles_m = cdiv(M, BM), p->P.counters = counters, p->P.dbg = nullptr;
     return p;
 }
 void chain_plan_destroy(ChainPlan *p) { delete p; }
@@ -390,7 +457,7 @@ int chain_plan_add_gemm(ChainPlan *pl, const ChainGemm &g) {
 int chain_plan_add_rows(ChainPlan *pl, const ChainRows &r) {
     ChainParams &P = pl->P;
     WB_ARG(P.n_phases < CHAIN_MAX_PHASES, "chain: too many phases");
-    WB_ARG(P.D % 128 == 0 && P.D <= 1024, "chain: D=%d must be a multiple of 128 and <= 1024", P.D);
+    WB_ARG(P.D % 128 == 0 && P.D <= 768, "chain: D=%d must be a multiple of 128 and <= 768", P.D);
     WB_ARG(r.x && (!r.gamma || (r.beta && r.xn)) && (r.embed ? (r.tok_emb && r.pos_emb && r.cur_tok && r.pos_dev) : (r.n_split == 0 || r.part)),
            "chain: bad row phase");
     ChainPhase &ph = P.ph[P.n_phases];
@@ -405,12 +472,62 @@ int chain_plan_add_rows(ChainPlan *pl, const ChainRows &r) {
     return WB_OK;
 }
 
+// WB_CHAIN_DBG=1: every launch records CTA 0's timestamps; chain_debug_dump prints those of the LAST launch
+static unsigned long long *g_chain_dbg = nullptr;
+static int g_chain_dbg_phases = 0;
+void chain_debug_dump() {
+    if (!g_chain_dbg) return;
+    cudaDeviceSynchronize();
+    const size_t n = (size_t)CHAIN_MAX_PHASES * 3 * 8;
+    std::vector<unsigned long long> h(n);
+    if (cudaMemcpy(h.data(), g_chain_dbg, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < n; i++)
+        if (h[i] && h[i] < t0) t0 = h[i];
+    fprintf(stderr, "chain timestamps of the last launch, CTA 0, first tile / unit of each phase (us since the first stamp)\n"
+                    "phase | producer: start B_issued dep_ready A_issued | mma: first_full commit | epi/rows: ready stored signalled\n");
+    for (int p = 0; p < g_chain_dbg_phases; p++) {
+        fprintf(stderr, "%5d |", p);
+        for (int r = 0; r < 3; r++) {
+            const int ne = r == 0 ? 4 : (r == 1 ? 2 : 3);
+            for (int e = 0; e < ne; e++) {
+                const unsigned long long v = h[((size_t)p * 3 + r) * 8 + e];
+                if (v) fprintf(stderr, " %8.2f", (double)(v - t0) / 1e3);
+                else fprintf(stderr, "        -");
+            }
+            fprintf(stderr, " |");
+        }
+        fprintf(stderr, "\n");
+    }
+}
+
 int chain_launch(cudaStream_t st, const ChainPlan *pl) {
     WB_ARG(pl && pl->P.n_phases > 0, "chain: empty plan");
+    static const bool dbg_on = getenv("WB_CHAIN_DBG") != nullptr;
+    ChainParams Pd;
+    const ChainParams *Pp = &pl->P;
+    if (dbg_on) {
+        if (!g_chain_dbg && cudaMalloc((void **)&g_chain_dbg, (size_t)CHAIN_MAX_PHASES * 3 * 8 * 8) != cudaSuccess) g_chain_dbg = nullptr;
+        if (g_chain_dbg) {
+            cudaMemsetAsync(g_chain_dbg, 0, (size_t)CHAIN_MAX_PHASES * 3 * 8 * 8, st);
+            Pd = pl->P, Pd.dbg = g_chain_dbg, Pp = &Pd;
+            g_chain_dbg_phases = pl->P.n_phases;
+        }
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    WB_CUDA(ensure_dyn_smem(decode_chain_kernel, TC_SMEM_BYTES));
+    void (*kernel)(const ChainParams) = nullptr;
+    switch (pl->P.D >> 7) {
+        case 1: kernel = decode_chain_kernel<1>; break;
+        case 2: kernel = decode_chain_kernel<2>; break;
+        case 3: kernel = decode_chain_kernel<3>; break;
+        case 4: kernel = decode_chain_kernel<4>; break;
+        case 5: kernel = decode_chain_kernel<5>; break;
+        case 6: kernel = decode_chain_kernel<6>; break;
+        default: set_error("chain: d_model %d not supported", pl->P.D); return WB_ERR_ARG;
+    }
+    WB_CUDA(ensure_dyn_smem(kernel, TC_SMEM_BYTES));
     // Cooperative launch: the whole grid is resident at once (one CTA per SM), which the arrival counters need --
     // also when another stream's kernels compete for the SMs.
     cudaLaunchConfig_t cfg = {};
@@ -420,7 +537,7 @@ int chain_launch(cudaStream_t st, const ChainPlan *pl) {
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    WB_CUDA(cudaLaunchKernelEx(&cfg, decode_chain_kernel, pl->P));
+    WB_CUDA(cudaLaunchKernelEx(&cfg, kernel, *Pp));
     WB_LAUNCHED();
     return WB_OK;
 }

@@ -65,5 +65,7 @@ size_t chain_counter_ints(int M);
 int chain_launch(cudaStream_t st, const ChainPlan *p);
 // Split-K factor for a residual GEMM with reduction length K (a property of the model, never of the batch size).
 int chain_split_k(int K);
+// Development aid: with WB_CHAIN_DBG set in the environment, prints CTA 0's per-phase timestamps of the last launch.
+void chain_debug_dump();
 
 }  // namespace wb

@@ -136,6 +136,7 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
 void model_destroy(Model *m) {
     if (!m) return;
     cudaStreamSynchronize(m->stream);
+    if (getenv("WB_CHAIN_DBG")) chain_debug_dump();
     if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->tr_cache) cache_destroy(m->tr_cache);
     cudaFree(m->tr_mel);
@@ -591,7 +592,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     // cache-wide segment sizes; this lane's chunks start b_off rows into every segment
     const size_t self_seg = (size_t)c->B * c->T * D, cross_seg = (size_t)c->B * m->S * D;
     const size_t self_off = (size_t)ln.b_off * c->T * D, cross_off = (size_t)ln.b_off * m->S * D;
-    const bool fused = m->decode_fused && impl == GEMM_IMPL_TC && c->lanes.size() == 1;
+    const bool fused = m->decode_fused && impl == GEMM_IMPL_TC && c->lanes.size() == 1 && D <= 768;
     if (fused && ln.plans.empty()) WB_CHECK(build_chain_plans(c, ln));  // host-only work (tensor maps): capture safe
     if (fused) {
         // 4 L + 3 kernels: chain | self-attn | chain | cross-attn | chain | ... | logits+argmax | argmax reduce

@@ -27,11 +27,17 @@ int make_tmap_h16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, 
                   uint64_t stride2_elems, uint32_t box_rows, int rank);  // gemm.cu
 
 enum { PH_GEMM = 0, PH_ROWS = 1 };
+// 4 ring stages of 32 KB + one 4 KB output staging tile per epilogue warp and 32-column chunk (TMA stores)
+static constexpr int CH_STAGES = 4;
+static constexpr int CH_STAGE_OUT_BYTES = 8 * 2 * 4096;
+static constexpr int CH_SMEM_BYTES = 1024 + CH_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + CH_STAGE_OUT_BYTES + 256 + 8 * 128 * 4;
 static constexpr int UNIT_ROWS = 8;  // rows per unit of a row phase: one per epilogue warp
 
 struct ChainPhase {
     CUtensorMap a_map;  // A [M][K], box {64, 128}
     CUtensorMap b_map;  // W [N][K], box {64, 128}
+    CUtensorMap o_map;  // tma_out: output as {N, M, splits}, box {32, 32, 1} (fp32: 128B swizzle, 16-bit: 64B swizzle)
+    int tma_out;        // plain [rows][N] output: coalesced bulk tensor stores instead of per-thread row stores
     GemmDev d;          // rows_per_batch = M, batches = split_k ("batch" b = K slice), num_kb per slice
     int type, tiles_n, splits;
     // row phase
@@ -125,34 +131,39 @@ __device__ __forceinline__ void chain_rows(const ChainPhase &ph, int row0, int M
     } else {
         const long long split_stride = (long long)M * D;
         // every load of both rows is issued before the first use: one L2 round trip, not one per slice
-        float4 pp[R][NV];
+        constexpr int SB = 4;  // slices whose loads are in flight together: one L2 round trip per 4 slices, not per slice
+        float4 pp[SB][R][NV];
 #pragma unroll
         for (int r = 0; r < R; r++)
 #pragma unroll
             for (int i = 0; i < NV; i++)
                 if (i < nvec && row0 + r < M) v[r][i] = reinterpret_cast<const float4 *>(ph.x + (size_t)(row0 + r) * D)[i * 32 + lane];
-        for (int s = 0; s < ph.n_split; s++) {  // fixed order: deterministic, batch independent
+        for (int s0 = 0; s0 < ph.n_split; s0 += SB) {
 #pragma unroll
-            for (int r = 0; r < R; r++)
+            for (int k = 0; k < SB; k++)
 #pragma unroll
-                for (int i = 0; i < NV; i++)
-                    if (i < nvec && row0 + r < M)
-                        // written by other CTAs of this launch, and rewritten by a later phase of it: ld.global.cg, so
-                        // a stale L1 line from an earlier read of these addresses on this SM cannot be hit
-                        pp[r][i] = __ldcg(reinterpret_cast<const float4 *>(ph.part + (size_t)s * split_stride + (size_t)(row0 + r) * D) + i * 32 + lane);
+                for (int r = 0; r < R; r++)
 #pragma unroll
-            for (int r = 0; r < R; r++)
+                    for (int i = 0; i < NV; i++)
+                        if (s0 + k < ph.n_split && row0 + r < M)
+                            // written by other CTAs of this launch, and rewritten by a later phase of it: ld.global.cg, so
+                            // a stale L1 line from an earlier read of these addresses on this SM cannot be hit
+                            pp[k][r][i] = __ldcg(reinterpret_cast<const float4 *>(ph.part + (size_t)(s0 + k) * split_stride + (size_t)(row0 + r) * D) + i * 32 + lane);
 #pragma unroll
-                for (int i = 0; i < NV; i++)
-                    if (i < nvec && row0 + r < M) {
-                        float4 a = v[r][i];
-                        if (s == 0 && ph.rbias) {  // x + bias first, then the slices in order (as resid_ln)
-                            const float4 c = __ldg(reinterpret_cast<const float4 *>(ph.rbias) + i * 32 + lane);
-                            a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
+            for (int k = 0; k < SB; k++)  // fixed order: x + bias, then the slices in order (as resid_ln): deterministic
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int i = 0; i < NV; i++)
+                        if (s0 + k < ph.n_split && row0 + r < M) {
+                            float4 a = v[r][i];
+                            if (s0 + k == 0 && ph.rbias) {
+                                const float4 c = __ldg(reinterpret_cast<const float4 *>(ph.rbias) + i * 32 + lane);
+                                a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
+                            }
+                            a.x += pp[k][r][i].x, a.y += pp[k][r][i].y, a.z += pp[k][r][i].z, a.w += pp[k][r][i].w;
+                            v[r][i] = a;
                         }
-                        a.x += pp[r][i].x, a.y += pp[r][i].y, a.z += pp[r][i].z, a.w += pp[r][i].w;
-                        v[r][i] = a;
-                    }
         }
 #pragma unroll
         for (int r = 0; r < R; r++)
@@ -217,16 +228,19 @@ __device__ __forceinline__ void chain_epilogue(const GemmDev &p, int b, int m, i
 
 // NV = d_model / 128 (the row phases keep a row in registers).
 template <int NV>
-__global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __maxnreg__(200) decode_chain_kernel(const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = tiles;
+    constexpr int STAGES = CH_STAGES;
+    constexpr int RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
     uint8_t *smem_b = tiles + STAGES * A_STAGE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint8_t *stage_out = tiles + RING_BYTES;  // [8 warps][2 chunks][4 KB], 1024-byte aligned (swizzled TMA source)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + RING_BYTES + CH_STAGE_OUT_BYTES);
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES;
     uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + 2;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
-    float *bias_smem = reinterpret_cast<float *>(tiles + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256);  // [8][128]
+    float *bias_smem = reinterpret_cast<float *>(tiles + RING_BYTES + CH_STAGE_OUT_BYTES + 256);  // [8][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = (int)gridDim.x;
@@ -236,6 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
             if (P.ph[p].type == PH_GEMM) {
                 ptx::prefetch_tmap(&P.ph[p].a_map);
                 ptx::prefetch_tmap(&P.ph[p].b_map);
+                if (P.ph[p].tma_out) ptx::prefetch_tmap(&P.ph[p].o_map);
             }
         for (int s = 0; s < STAGES; s++) {
             ptx::mbar_init(&full_bar[s], 1);
@@ -360,18 +375,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_relaxed(&tmem_empty[acc]);  // accumulator is in registers
-                    switch (d.epi) {
-                        case EPI_GELU_H16: chain_epilogue<EPI_GELU_H16>(d, sp, m, n_first, v0, v1, sbias); break;
-                        case EPI_STORE_F32: chain_epilogue<EPI_STORE_F32>(d, sp, m, n_first, v0, v1, sbias); break;
-                        default: chain_epilogue<EPI_STORE_H16>(d, sp, m, n_first, v0, v1, sbias); break;
-                    }
-                    if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 1);
-                    if (signal) {
-                        // every lane's stores -> (generic -> async proxy fence) -> warp barrier -> one releasing
-                        // reduction at gpu scope: the release is cumulative over the lanes the barrier ordered before it
-                        fence_proxy_async_all();
+                    if (ph.tma_out) {
+                        // 32 rows x 32 values per chunk -> this warp's staging tile, 16-byte pieces XOR-swizzled as the
+                        // output tensor map expects, then ONE bulk tensor store per chunk: full-line writes instead of
+                        // 32 scattered row stores per instruction (those took 4 us per tile and another 2-4 us until
+                        // the releasing signal had drained them; timestamps in profiles/).  Rows / columns outside
+                        // [M, N) are clipped by the tensor map.
+                        const int m_w = mt * BM + q * 32;
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            const uint32_t *vv = c ? v1 : v0;
+                            uint8_t *buf = stage_out + (ew * 2 + c) * 4096;
+                            float o[32];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float4 bv = *reinterpret_cast<const float4 *>(sbias + c * 32 + 4 * j);
+                                o[4 * j] = __uint_as_float(vv[4 * j]) + bv.x, o[4 * j + 1] = __uint_as_float(vv[4 * j + 1]) + bv.y;
+                                o[4 * j + 2] = __uint_as_float(vv[4 * j + 2]) + bv.z, o[4 * j + 3] = __uint_as_float(vv[4 * j + 3]) + bv.w;
+                            }
+                            if (d.epi == EPI_STORE_F32) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++)
+                                    *reinterpret_cast<float4 *>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                        make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                            } else {
+                                if (d.epi == EPI_GELU_H16) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 2) {
+                                        const float2 gl = gelu_fast2(make_float2(o[j], o[j + 1]));
+                                        o[j] = gl.x, o[j + 1] = gl.y;
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    *reinterpret_cast<uint4 *>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                                        make_uint4(pack_h2(o[8 * j], o[8 * j + 1]), pack_h2(o[8 * j + 2], o[8 * j + 3]),
+                                                   pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7]));
+                            }
+                        }
+                        ptx::fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) chain_signal(ctr + mt);
+                        if (lane == 0) {
+                            ptx::tma_store_3d(&ph.o_map, stage_out + (ew * 2) * 4096, n_first, m_w, sp);
+                            ptx::tma_store_3d(&ph.o_map, stage_out + (ew * 2 + 1) * 4096, n_first + 32, m_w, sp);
+                            ptx::bulk_commit_group();
+                            ptx::bulk_wait_group<0>();  // written (not just read): the staging tiles are free and the data can be signalled
+                        }
+                        if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 1);
+                        if (signal) {
+                            if (lane == 0) {
+                                fence_proxy_async_all();
+                                chain_signal(ctr + mt);
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        switch (d.epi) {
+                            case EPI_GELU_H16: chain_epilogue<EPI_GELU_H16>(d, sp, m, n_first, v0, v1, sbias); break;
+                            case EPI_STORE_F32: chain_epilogue<EPI_STORE_F32>(d, sp, m, n_first, v0, v1, sbias); break;
+                            default: chain_epilogue<EPI_STORE_H16>(d, sp, m, n_first, v0, v1, sbias); break;
+                        }
+                        if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 1);
+                        if (signal) {
+                            // every lane's stores -> (generic -> async proxy fence) -> warp barrier -> one releasing
+                            // reduction at gpu scope: the release is cumulative over the lanes the barrier ordered before it
+                            fence_proxy_async_all();
+                            __syncwarp();
+                            if (lane == 0) chain_signal(ctr + mt);
+                        }
                     }
                     if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 2);
                 }
@@ -401,6 +472,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
 }
+
+int make_tmap_any_pub(CUtensorMap *map, CUtensorMapDataType dtype, int swizzle_bytes, const void *base, int rank,
+                      const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box);  // gemm.cu
 
 // ---------------------------------------------------------------------------------------------
 // Host side
@@ -449,6 +523,18 @@ int chain_plan_add_gemm(ChainPlan *pl, const ChainGemm &g) {
     d.n_seg_ptrs = g.n_seg_ptrs;
     d.dyn_off = g.dyn_off;
     WB_ARG(d.out[0] && (d.seg_cols == g.N || d.seg_cols % 32 == 0), "chain: bad output routing");
+    // plain [rows][N] outputs go through TMA stores (fp32 partials, q', h); segmented / cache-offset outputs keep the
+    // per-thread stores
+    const int esz = g.epi == EPI_STORE_F32 ? 4 : 2;
+    ph.tma_out = g.n_seg_ptrs == 1 && !g.dyn_off && d.seg_cols == g.N && (g.out_ld[0] * esz) % 16 == 0 &&
+                 (reinterpret_cast<uintptr_t>(g.out[0]) & 15) == 0;
+    if (ph.tma_out) {
+        const uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)P.M, (uint64_t)g.split_k};
+        const uint64_t str[2] = {(uint64_t)g.out_ld[0] * esz, (uint64_t)P.M * g.out_ld[0] * esz};
+        const uint32_t box[3] = {32, 32, 1};
+        WB_CHECK(make_tmap_any_pub(&ph.o_map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : H16_TMAP_DTYPE, esz == 4 ? 128 : 64,
+                                   g.out[0], 3, dims, str, box));
+    }
     P.n_phases++;
     pl->grid = std::max(pl->grid, P.tiles_m * ph.tiles_n * ph.splits);
     return WB_OK;
@@ -527,12 +613,12 @@ int chain_launch(cudaStream_t st, const ChainPlan *pl) {
         case 6: kernel = decode_chain_kernel<6>; break;
         default: set_error("chain: d_model %d not supported", pl->P.D); return WB_ERR_ARG;
     }
-    WB_CUDA(ensure_dyn_smem(kernel, TC_SMEM_BYTES));
+    WB_CUDA(ensure_dyn_smem(kernel, CH_SMEM_BYTES));
     // Cooperative launch: the whole grid is resident at once (one CTA per SM), which the arrival counters need --
     // also when another stream's kernels compete for the SMs.
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(std::min(pl->grid, sms)), cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM_BYTES, cfg.stream = st;
+    cfg.dynamicSmemBytes = CH_SMEM_BYTES, cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;

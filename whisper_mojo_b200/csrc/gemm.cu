@@ -533,6 +533,10 @@ static int make_tmap_any(CUtensorMap *map, CUtensorMapDataType dtype, int swizzl
     }
     return WB_OK;
 }
+int make_tmap_any_pub(CUtensorMap *map, CUtensorMapDataType dtype, int swizzle_bytes, const void *base, int rank,
+                      const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
+    return make_tmap_any(map, dtype, swizzle_bytes, base, rank, dims, strides_bytes, box);
+}
 // fp32 tensor map, 128-byte swizzle (box[0] = 32 elements).
 int make_tmap_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
                   const uint32_t *box) {

@@ -631,16 +631,12 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     //    LayerNorm kernel sums them into x in a fixed order first -- same number of launches, whole chip busy.
     auto resid_gemm_ln = [&](int cat, const h16 *A, int K, const h16 *Wt, const float *bias, const float *g,
                              const float *bb) -> int {
-        int split = 1;
-        // the split is a property of the model, never of the batch size: a chunk's fp32 sums (hence its ids at
-        // low-margin steps) must not depend on how many other chunks share the wave (bench parity.cross_g)
-        if (impl == GEMM_IMPL_TC && ln.part && m->decode_split_k >= 1)
-            for (int sp : {4, 3, 2})
-                if (K % (64 * sp) == 0 && K / sp >= 192) {
-                    split = sp;
-                    break;
-                }
-        if (split > 1) {
+        // The same K slices, summed in the same order, as the chain kernels use (chain_split_k: a property of the
+        // model, never of the batch size), including the one-slice case: x + bias + part[0] + part[1] + ..., so this
+        // kernel-per-op form and the fused form produce the same bits, and a chunk's fp32 sums (hence its ids at
+        // low-margin steps) do not depend on how many other chunks share the wave.
+        if (impl == GEMM_IMPL_TC && ln.part && m->decode_split_k >= 1) {
+            const int split = chain_split_k(K);
             GemmDesc gd = plain_gemm(A, B, K, Wt, D, nullptr, EPI_STORE_F32, ln.part, D);
             gd.split_k = split;
             WB_CHECK(timed_kernel(m, st, cat, [&] { return gemm_run(st, gd, impl); }));

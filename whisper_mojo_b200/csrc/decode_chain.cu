@@ -228,7 +228,7 @@ __device__ __forceinline__ void chain_epilogue(const GemmDev &p, int b, int m, i
 
 // NV = d_model / 128 (the row phases keep a row in registers).
 template <int NV>
-__global__ void __maxnreg__(200) decode_chain_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __maxnreg__(192) decode_chain_kernel(const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = tiles;

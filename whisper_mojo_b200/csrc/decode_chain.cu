@@ -131,7 +131,7 @@ __device__ __forceinline__ void chain_rows(const ChainPhase &ph, int row0, int M
     } else {
         const long long split_stride = (long long)M * D;
         // every load of both rows is issued before the first use: one L2 round trip, not one per slice
-        constexpr int SB = 4;  // slices whose loads are in flight together: one L2 round trip per 4 slices, not per slice
+        constexpr int SB = NV <= 3 ? 4 : 2;  // slices whose loads are in flight together (one L2 round trip per SB slices)
         float4 pp[SB][R][NV];
 #pragma unroll
         for (int r = 0; r < R; r++)
@@ -228,7 +228,7 @@ __device__ __forceinline__ void chain_epilogue(const GemmDev &p, int b, int m, i
 
 // NV = d_model / 128 (the row phases keep a row in registers).
 template <int NV>
-__global__ void __maxnreg__(192) decode_chain_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = tiles;

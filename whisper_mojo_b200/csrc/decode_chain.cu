@@ -38,6 +38,8 @@ struct ChainPhase {
     CUtensorMap b_map;  // W [N][K], box {64, 128}
     CUtensorMap o_map;  // tma_out: output as {N, M, splits}, box {32, 32, 1} (fp32: 128B swizzle, 16-bit: 64B swizzle)
     int tma_out;        // plain [rows][N] output: coalesced bulk tensor stores instead of per-thread row stores
+    const void *w_base;  // the phase's weight matrix, for the L2 prefetch at kernel start
+    unsigned long long w_bytes;
     GemmDev d;          // rows_per_batch = M, batches = split_k ("batch" b = K slice), num_kb per slice
     int type, tiles_n, splits;
     // row phase
@@ -84,6 +86,11 @@ __device__ __forceinline__ void chain_wait(const int *ctr, int target) {
 }
 __device__ __forceinline__ void chain_signal(int *ctr) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ctr), "r"(1) : "memory");
+}
+// After cp.async.bulk.wait_group 0 the bulk stores ARE performed: nothing of this thread is in flight, so the arrival
+// needs no release fence (a releasing reduction costs a MEMBAR.GPU, 1.5-3 us under load: timestamps in profiles/)
+__device__ __forceinline__ void chain_signal_relaxed(int *ctr) {
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(ctr), "r"(1) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -244,7 +251,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = (int)gridDim.x;
+    if (P.dbg && threadIdx.x == 0 && blockIdx.x < 256) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + blockIdx.x] = ptx::globaltimer_ns();
 
+    if (warp == 2) {
+        // The attention kernel that ran before this one streamed gigabytes through the L2, so every weight matrix of
+        // this chain is cold; its first reader would pay the HBM latency per ring refill (4 x 32 KB in flight per SM
+        // = ~75 GB/s per SM, measured).  Each CTA asks the L2 for its 1/G slice of every matrix of the chain right
+        // away, so the later phases' weights arrive while the first phases run.
+        for (int p = 0; p < P.n_phases; p++) {
+            const ChainPhase &ph = P.ph[p];
+            if (ph.type != PH_GEMM || !ph.w_bytes) continue;
+            const unsigned long long per = ((ph.w_bytes / G) + 4095ull) & ~4095ull;  // 4 KB pieces, one per lane and round
+            const unsigned long long lo = per * blockIdx.x, hi = lo + per < ph.w_bytes ? lo + per : ph.w_bytes;
+            for (unsigned long long off = lo + 4096ull * lane; off < hi; off += 4096ull * 32) {
+                const unsigned n = (unsigned)(hi - off < 4096ull ? hi - off : 4096ull) & ~15u;
+                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(ph.w_base) + off), "r"(n) : "memory");
+            }
+        }
+    }
     if (warp == 0 && lane == 0) {
         for (int p = 0; p < P.n_phases; p++)
             if (P.ph[p].type == PH_GEMM) {
@@ -423,10 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                         }
                         if (t == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 1);
                         if (signal) {
-                            if (lane == 0) {
-                                fence_proxy_async_all();
-                                chain_signal(ctr + mt);
-                            }
+                            if (lane == 0) chain_signal_relaxed(ctr + mt);
                         }
                         __syncwarp();
                     } else {
@@ -470,6 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (P.dbg && threadIdx.x == 0 && blockIdx.x < 256) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + 256 + blockIdx.x] = ptx::globaltimer_ns();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
 }
 
@@ -510,6 +532,7 @@ int chain_plan_add_gemm(ChainPlan *pl, const ChainGemm &g) {
     ph.type = PH_GEMM;
     ph.tiles_n = cdiv(g.N, BN);
     ph.splits = g.split_k;
+    ph.w_base = g.W, ph.w_bytes = (unsigned long long)g.N * g.K * sizeof(h16);
     WB_CHECK(make_tmap_h16(&ph.a_map, g.A, (uint64_t)g.K, (uint64_t)P.M, 1, (uint64_t)g.K, 0, BM, 2));
     WB_CHECK(make_tmap_h16(&ph.b_map, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.K, 0, BN, 2));
     GemmDev &d = ph.d;
@@ -564,12 +587,21 @@ static int g_chain_dbg_phases = 0;
 void chain_debug_dump() {
     if (!g_chain_dbg) return;
     cudaDeviceSynchronize();
-    const size_t n = (size_t)CHAIN_MAX_PHASES * 3 * 8;
+    const size_t n = (size_t)CHAIN_MAX_PHASES * 3 * 8 + 512;
     std::vector<unsigned long long> h(n);
     if (cudaMemcpy(h.data(), g_chain_dbg, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
-    unsigned long long t0 = ~0ull;
-    for (size_t i = 0; i < n; i++)
-        if (h[i] && h[i] < t0) t0 = h[i];
+    unsigned long long t0 = ~0ull, s_max = 0, e_min = ~0ull, e_max = 0;
+    const size_t np_ = (size_t)CHAIN_MAX_PHASES * 3 * 8;
+    int n_cta = 0;
+    for (size_t i = 0; i < 256; i++)
+        if (h[np_ + i]) {
+            n_cta++;
+            t0 = std::min(t0, h[np_ + i]), s_max = std::max(s_max, h[np_ + i]);
+            e_min = std::min(e_min, h[np_ + 256 + i]), e_max = std::max(e_max, h[np_ + 256 + i]);
+        }
+    fprintf(stderr, "%d CTAs: started within %.2f us, ended between %.2f and %.2f us after the first start (CTA 0: %.2f .. %.2f)\n", n_cta,
+            (double)(s_max - t0) / 1e3, (double)(e_min - t0) / 1e3, (double)(e_max - t0) / 1e3, (double)(h[np_] - t0) / 1e3,
+            (double)(h[np_ + 256] - t0) / 1e3);
     fprintf(stderr, "chain timestamps of the last launch, CTA 0, first tile / unit of each phase (us since the first stamp)\n"
                     "phase | producer: start B_issued dep_ready A_issued | mma: first_full commit | epi/rows: ready stored signalled\n");
     for (int p = 0; p < g_chain_dbg_phases; p++) {
@@ -593,9 +625,9 @@ int chain_launch(cudaStream_t st, const ChainPlan *pl) {
     ChainParams Pd;
     const ChainParams *Pp = &pl->P;
     if (dbg_on) {
-        if (!g_chain_dbg && cudaMalloc((void **)&g_chain_dbg, (size_t)CHAIN_MAX_PHASES * 3 * 8 * 8) != cudaSuccess) g_chain_dbg = nullptr;
+        if (!g_chain_dbg && cudaMalloc((void **)&g_chain_dbg, ((size_t)CHAIN_MAX_PHASES * 3 * 8 + 512) * 8) != cudaSuccess) g_chain_dbg = nullptr;
         if (g_chain_dbg) {
-            cudaMemsetAsync(g_chain_dbg, 0, (size_t)CHAIN_MAX_PHASES * 3 * 8 * 8, st);
+            cudaMemsetAsync(g_chain_dbg, 0, ((size_t)CHAIN_MAX_PHASES * 3 * 8 + 512) * 8, st);
             Pd = pl->P, Pd.dbg = g_chain_dbg, Pp = &Pd;
             g_chain_dbg_phases = pl->P.n_phases;
         }

@@ -449,6 +449,58 @@ __global__ void greedy_advance_kernel(GreedyState g, int B, int mode, int next_p
         g.scalars[1] = (mode == 0) ? cl : cl - g.pos_quirk;
     }
 }
+// argmax over the logits GEMM's per-tile partials (first index of the row maximum, whisper_tensor.mojo:431-439) fused
+// with the greedy bookkeeping of the row: one kernel instead of argmax_partials + greedy_advance.  Warp per row.
+__global__ void greedy_argmax_advance_kernel(GreedyState g, int B, const float *__restrict__ part_val,
+                                             const int *__restrict__ part_idx, int tiles_n, int *__restrict__ next) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row < B) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int t = lane; t < tiles_n; t += 32) {
+            const float v = part_val[(size_t)row * tiles_n + t];
+            const int i = part_idx[(size_t)row * tiles_n + t];
+            if (v > best || (v == best && i < bi)) best = v, bi = i;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+        }
+        if (lane == 0) {
+            const int tok = (bi == 0x7fffffff) ? 0 : bi;
+            next[row] = tok;
+            if (!g.done[row]) {
+                const int n = g.out_len[row];
+                if (n < g.T_out) {
+                    g.tokens_out[(size_t)row * g.T_out + n] = tok;
+                    g.out_len[row] = n + 1;
+                }
+                if (tok == g.eot) {
+                    g.done[row] = 1;
+                    atomicAdd(&g.scalars[2], 1);
+                }
+            }
+            g.cur_tok[row] = tok;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // no thread of this launch reads the scalars (see greedy_advance_kernel)
+        const int cl = g.scalars[0] + 1;
+        g.scalars[0] = cl;
+        g.scalars[1] = cl - g.pos_quirk;  // generated tokens use current_len - quirk (whisper.mojo:217)
+    }
+}
+int greedy_argmax_advance(cudaStream_t st, const GreedyState &g, int B, const float *part_val, const int *part_idx,
+                          int tiles_n, int *next) {
+    if (B <= 0) return WB_OK;
+    WB_CUDA(launch_pdl(greedy_argmax_advance_kernel, dim3(cdiv(B, 8)), dim3(256), 0, st, g, B, part_val, part_idx, tiles_n, next));
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
 int greedy_advance(cudaStream_t st, const GreedyState &g, int B, int mode, int next_prompt_token, const int *next) {
     WB_CUDA(launch_pdl(greedy_advance_kernel, dim3(cdiv(B, 256)), dim3(256), 0, st, g, B, mode, next_prompt_token, next));
     WB_LAUNCHED();

@@ -75,6 +75,9 @@ struct GreedyState {
 int greedy_init(cudaStream_t st, const GreedyState &g, int B, const int *prompt4_host);
 // mode 0: prefill advance (feed prompt[next_prompt_idx] next); mode 1: greedy append from `next`.
 int greedy_advance(cudaStream_t st, const GreedyState &g, int B, int mode, int next_prompt_token, const int *next);
+// argmax over the EPI_ARGMAX partials of the logits GEMM + the mode-1 bookkeeping above, in one kernel.
+int greedy_argmax_advance(cudaStream_t st, const GreedyState &g, int B, const float *part_val, const int *part_idx,
+                          int tiles_n, int *next);
 
 // ---- frontend (frontend.cu) ------------------------------------------------------------------
 struct FrontendTables {

@@ -584,7 +584,7 @@ static int timed_kernel(Model *m, cudaStream_t st, int category, Fn launch) {
 
 // One decoder forward with q_len = 1 for every chunk of the cache (whisper.mojo:130-167,
 // layers.mojo:435-519 with is_decoder = True).  Token / position / cur_len come from device memory.
-int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits) {
+int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits, bool advance) {
     Model *m = c->m;
     const int B = ln.B, D = m->D, impl = m->gemm_impl;
     const float *W = m->w32;
@@ -706,6 +706,8 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         WB_ARG(!(store_logits || impl == GEMM_IMPL_REF) || ln.logits, "decode_step: cache has no logits buffer");
         WB_CHECK(timed_kernel(m, st, TK_LOGITS, [&] { return gemm_run(st, g, impl); }));
         WB_CHECK(timed_kernel(m, st, TK_MISC, [&] {
+            // greedy loop: argmax + append / EOT / position bookkeeping in one kernel (whisper.mojo:198-221)
+            if (advance) return greedy_argmax_advance(st, ln.g, B, ln.part_val, ln.part_idx, gemm_tiles_n(m->V), ln.next);
             return argmax_partials(st, ln.part_val, ln.part_idx, B, gemm_tiles_n(m->V), ln.next);
         }));
     }
@@ -727,8 +729,9 @@ static int step_all_lanes(Cache *c, bool with_logits, int mode, int next_prompt_
     for (size_t i = 0; i < c->lanes.size(); i++) {
         Lane &ln = c->lanes[i];
         cudaStream_t st = i == 0 ? m->stream : m->stream2;
-        WB_CHECK(decode_step(c, ln, st, with_logits, false));
-        WB_CHECK(greedy_advance(st, ln.g, ln.B, mode, next_prompt_token, ln.next));
+        const bool fused_adv = with_logits && mode == 1;
+        WB_CHECK(decode_step(c, ln, st, with_logits, false, fused_adv));
+        if (!fused_adv) WB_CHECK(greedy_advance(st, ln.g, ln.B, mode, next_prompt_token, ln.next));
     }
     if (two) {
         WB_CUDA(cudaEventRecord(m->ev_join, m->stream2));
@@ -975,7 +978,7 @@ int cache_step_api(Cache *c, const int32_t *tokens_host, int start_pos, float *l
     Lane &ln = c->lanes[0];
     WB_ARG(!logits_host || ln.logits, "decode_step: cache was created without a logits buffer");
     WB_CHECK(set_step_state(c, c->host_len, start_pos, tokens_host));
-    WB_CHECK(decode_step(c, ln, m->stream, true, logits_host != nullptr));
+    WB_CHECK(decode_step(c, ln, m->stream, true, logits_host != nullptr, false));
     c->host_len++;
     if (logits_host)
         WB_CUDA(cudaMemcpyAsync(logits_host, ln.logits, (size_t)c->B * m->V * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -998,7 +1001,7 @@ int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_
         for (int b = 0; b < n; b++) col[b] = forced_host[(size_t)b * n_forced + i];
         const int pos = i < 4 ? i : i - m->cfg.pos_quirk;  // whisper.mojo:196,217
         rc = set_step_state(c, i, pos, col.data());
-        if (rc == WB_OK) rc = decode_step(c, ln, m->stream, i >= 3, i >= 3);
+        if (rc == WB_OK) rc = decode_step(c, ln, m->stream, i >= 3, i >= 3, false);
         if (rc == WB_OK && i >= 3) {
             // logits_host is [n][n_forced-3][V]; this step is row i-3 of every chunk
             cudaError_t e = cudaMemcpy2DAsync(logits_host + (size_t)(i - 3) * m->V,

@@ -143,7 +143,7 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
 void cache_destroy(Cache *c);
 int cache_reset(Cache *c);
 int cache_set_encoder(Cache *c, const float *enc_out_dev);
-int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits);
+int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits, bool advance);
 int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
                      int32_t *out_len_dev, const float *in_host = nullptr);
 int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_t *forced_host, int n_forced,

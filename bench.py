@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run id checks (cross-G subset, CPU oracle)")
     ap.add_argument("--parity-chunks", type=int, default=4, help="chunks checked against the CPU oracle after the timed run")
     ap.add_argument("--no-bf16", action="store_true", help="skip the bf16-build comparison run (N=1 only)")
+    ap.add_argument("--eot-schedule", default="40:195", help="lo:hi -- one extra untimed pass pair with declared chunk lengths ~U(lo, hi) "
+                    "(EOT never fires with random weights): decode time with / without skipping finished chunks; '' = off")
     ap.add_argument("--breakdown", action="store_true", help="add a per-kernel-category decode breakdown (one extra eager pass)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="tiny", choices=["tiny", "small"],
@@ -509,6 +511,30 @@ def run_b200(args):
         except Exception as ex:
             breakdown = {"error": str(ex)}
 
+    # ---- finished chunks (whisper.mojo:206-207): declared lengths, decode time with / without skipping them -------
+    eot_variant = None
+    if args.eot_schedule and not small:
+        try:
+            lo_l, hi_l = [int(x) for x in args.eot_schedule.split(":")]
+            lens_decl = np.random.default_rng(99).integers(lo_l, hi_l + 1, n_total).astype(np.int32)[lo:hi]
+            model.set_stop_lengths(lens_decl)
+            res = {}
+            for skip in (1, 0):
+                model.set_option("skip_done", skip)
+                model.transcribe_pcm_batch(pcm)
+                tk, lk = model.transcribe_pcm_batch(pcm)
+                torch.cuda.synchronize()
+                res[skip] = (model.last_timing()["decode_ms"], tk.cpu().numpy(), lk.cpu().numpy())
+            model.set_option("skip_done", 1)
+            model.set_stop_lengths(None)
+            eot_variant = {"declared_lengths": f"U({lo_l},{hi_l}) ids per chunk (wm_set_stop_lengths)", "mean_len": float(lens_decl.mean()),
+                           "live_chunk_steps_frac": float((lens_decl - 4).sum() / ((cfg.max_tokens - 4) * len(lens_decl))),
+                           "decode_ms_skip_done": res[1][0], "decode_ms_stream_all": res[0][0], "decode_ms_all_live": phases["decode_ms"],
+                           "ids_identical": bool(np.array_equal(res[1][1], res[0][1]) and np.array_equal(res[1][2], res[0][2])),
+                           "lengths_as_declared": bool(np.array_equal(res[1][2], lens_decl))}
+        except Exception as ex:
+            eot_variant = {"error": str(ex)[:300]}
+
     # ---- phase rooflines: encoder on the tensor pipe, whole decode step and frontend on HBM ----
     phase_roof = None
     try:
@@ -566,7 +592,7 @@ def run_b200(args):
             env = dict(os.environ, WB_PRECISION="bf16")
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(args.warmup),
                                 "--chunks", str(args.chunks), "--scaling", args.scaling, "--no-e2e", "--no-cpu-baseline",
-                                "--no-parity", "--no-bf16", "--sampler", "none"], env=env, capture_output=True, text=True, timeout=300)
+                                "--no-parity", "--no-bf16", "--sampler", "none", "--eot-schedule", ""], env=env, capture_output=True, text=True, timeout=300)
             b = json.loads(r.stdout.strip().splitlines()[-1])
             bf16_line = {"value": b["value"], "unit": UNIT, "ms_per_step": b["ms_per_step"], "dtype": b["dtype"],
                          "note": "libwhisper_b200_bf16.so (-DWB_BF16): enc_out / logits max-abs 2.7e-2 / 5.4e-2 vs the oracle, above north_star's 1e-2"}
@@ -592,6 +618,7 @@ def run_b200(args):
             "clocks": clocks, "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches), "roofline": roofline,
             "phase_rooflines": phase_roof, "parity": parity, "ids_sha256": ids_sha,
             "cpu_baseline": cpu, "cpu_baseline_hf_generate": cpu_hf, "bf16_variant": bf16_line, "decode_breakdown": breakdown,
+            "eot_schedule_variant": eot_variant,
             "phases_ms_per_step": phases, "device_ms_each_step": step_ms, "decode_ms_each_step": step_decode_ms,
         }
         def plain(o):  # numpy scalars that slipped into the record

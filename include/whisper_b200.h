@@ -148,7 +148,8 @@ int wm_weight_tensor(wm_model m, int index, void **dev_ptr, int64_t *n_floats);
  * latency-oriented decode: K/V-form cross-attention split over the SMs + programmatic dependent launch; default 0 = off,
  * 8 is a good value for batch-1 use), "decode_split_k" (split-K residual GEMMs + fused residual/LayerNorm in
  * the decode step: 0 = off, 1 = on (default); never a function of the batch size, so a chunk's ids do not depend
- * on how many chunks share its wave). */
+ * on how many chunks share its wave), "decode_fused" (1 = persistent chain kernels, 4 L + 3 launches per step
+ * (default); 0 = one kernel per op, 12 L + 4), "skip_done" (see wm_set_stop_lengths). */
 int wm_set_option(wm_model m, const char *key, int64_t value);
 
 /* Log-mel frontend (HF WhisperFeatureExtractor via export_weights.py:116): pcm f32 [n_chunks,
@@ -187,6 +188,13 @@ int wm_transcribe_dev(wm_model m, const float *mel_dev, int n_chunks, int32_t *o
 int wm_transcribe_pcm(wm_model m, const float *pcm_host, int n_chunks, int32_t *out_tokens_host, int32_t *out_len_host);
 int wm_transcribe_pcm_dev(wm_model m, const float *pcm_dev, int n_chunks, int32_t *out_tokens_dev,
                           int32_t *out_len_dev);
+
+/* Test / bench hook for `if next_token == 50257: break` (whisper.mojo:206-207).  With random weights EOT never wins,
+ * so chunk lengths can be DECLARED: for every later wm_transcribe* call the id that would bring chunk i's count to
+ * lens_host[i] (>= 5: 4 prompt ids + EOT) is replaced by EOT and the chunk finishes there.  n = 0 clears the schedule;
+ * chunks beyond n are unaffected.  Finished chunks drop out of the attention kernels (option "skip_done", default 1;
+ * 0 keeps streaming them until the whole wave is done, round 1's behaviour) -- ids are identical either way. */
+int wm_set_stop_lengths(wm_model m, const int32_t *lens_host, int n_chunks);
 
 /* Teacher-forced decode for parity tests: forced int32 [n_chunks, n_forced] (host); prefill with
  * forced[:, 0:4], then feed forced[:, 4:] with the greedy loop's start_pos rule; logits_host f32

@@ -601,3 +601,31 @@ def test_fused_decode_ragged_batches_are_batch_invariant():
         assert np.array_equal(t, t300[:n]) and np.array_equal(l, l300[:n]), n
     t2, _ = m.transcribe_batch(mel)
     assert np.array_equal(t2, t300)
+
+
+@pytest.mark.parametrize("n", [40, 300])
+def test_finished_chunks_are_skipped_without_changing_ids(n):
+    """`if next_token == 50257: break` (whisper.mojo:206-207), batched.  EOT never wins with random weights, so the
+    lengths are declared (wm_set_stop_lengths): chunk i must end with EOT at exactly that length, its earlier ids must
+    be those of the free-running decode, and dropping finished chunks from the attention kernels (skip_done = 1, the
+    default: live list rebuilt every 16 steps) must give the same ids as streaming them to the end (skip_done = 0)."""
+    cfg = WhisperConfig.micro()
+    m, _ = build(cfg)
+    mel = synth.make_mel(n, cfg, 41)
+    free, free_len = m.transcribe_batch(mel)
+    want = np.random.default_rng(5).integers(5, cfg.max_tokens + 1, n).astype(np.int32)
+    want[:3] = (5, cfg.max_tokens, 6)
+    m.set_stop_lengths(want)
+    t1, l1 = m.transcribe_batch(mel)
+    m.set_option("skip_done", 0)
+    t0, l0 = m.transcribe_batch(mel)
+    m.set_option("skip_done", 1)
+    assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
+    assert np.array_equal(l1, want)
+    for i in range(n):
+        assert t1[i, want[i] - 1] == cfg.eot and np.all(t1[i, want[i]:] == -1)
+        k = min(want[i] - 1, free_len[i])
+        assert np.array_equal(t1[i, :k], free[i, :k]), i
+    m.set_stop_lengths(None)
+    t2, l2 = m.transcribe_batch(mel)
+    assert np.array_equal(t2, free) and np.array_equal(l2, free_len)

@@ -75,6 +75,7 @@ SIGNATURES = {
     "wm_transcribe_dev": (c_int, [c_uint64, c_void_p, c_int, c_void_p, c_void_p]),
     "wm_transcribe_pcm": (c_int, [c_uint64, c_void_p, c_int, c_void_p, c_void_p]),
     "wm_transcribe_pcm_dev": (c_int, [c_uint64, c_void_p, c_int, c_void_p, c_void_p]),
+    "wm_set_stop_lengths": (c_int, [c_uint64, c_void_p, c_int]),
     "wm_teacher_forced": (c_int, [c_uint64, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "wm_last_timing": (c_int, [c_uint64, POINTER(c_float)]),
     "wm_last_kernel_timing": (c_int, [c_uint64, c_char_p, POINTER(c_float), POINTER(c_int64)]),

@@ -454,6 +454,14 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
         }
         m->decode_fused = (int)value;
     }
+    else if (!strcmp(key, "skip_done")) {
+        WB_ARG(value == 0 || value == 1, "skip_done must be 0 or 1");
+        if (m->skip_done != (int)value && m->tr_cache) {  // the captured decode graph holds the kernel arguments
+            cache_destroy(m->tr_cache);
+            m->tr_cache = nullptr;
+        }
+        m->skip_done = (int)value;
+    }
     else if (!strcmp(key, "use_graph")) m->use_graph = (int)value;
     else if (!strcmp(key, "profile_attn")) m->profile_attn = (int)value;
     else if (!strcmp(key, "cross_impl")) {
@@ -648,6 +656,20 @@ int wm_teacher_forced(wm_model h, const float *enc_out_dev, int n_chunks, const 
             WB_ARG(forced_host[i] >= 0 && forced_host[i] < m->V, "teacher_forced: token id %d out of range",
                    forced_host[i]);
     return model_teacher_forced(m, enc_out_dev, n_chunks, forced_host, n_forced, logits_host);
+}
+
+int wm_set_stop_lengths(wm_model h, const int32_t *lens_host, int n) {
+    MODEL(m, h);
+    WB_ARG(n >= 0 && (n == 0 || lens_host), "set_stop_lengths: bad arguments");
+    for (int i = 0; i < n; i++) WB_ARG(lens_host[i] >= 5, "set_stop_lengths: length %d of chunk %d is below 5 (4 prompt ids + EOT)", lens_host[i], i);
+    WB_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(m->stop_sched);
+    m->stop_sched = nullptr, m->stop_sched_n = 0;
+    if (n == 0) return WB_OK;
+    WB_CUDA(cudaMalloc((void **)&m->stop_sched, (size_t)n * sizeof(int)));
+    WB_CUDA(cudaMemcpy(m->stop_sched, lens_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    m->stop_sched_n = n;
+    return WB_OK;
 }
 
 int wm_stream(wm_model h, void **stream) {

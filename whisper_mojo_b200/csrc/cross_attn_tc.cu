@@ -51,6 +51,9 @@ struct CrossAttnParams {
     CUtensorMap q_map;    // dims (D, H, B), box (64, 16, 1): rows >= H are zero filled
     h16 *ctx;   // [B][H*D]
     int B, S, D, H, n_blocks, atoms;
+    // Finished chunks are skipped (whisper.mojo:206-207 `if next_token == 50257: break`, batched): when `live` is set the
+    // kernel walks live[0 .. *n_live) -- the indices of the chunks still decoding -- instead of 0 .. B.
+    const int *live, *n_live;
     unsigned long long *dbg;  // optional timestamp dump (CTA 0): [role][block][event]
 };
 
@@ -191,12 +194,14 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
     const uint32_t tS0 = tmem_base, tC0 = tmem_base + 32 * n_acc;
     constexpr int C_BUF = 16 * n_acc;  // columns of one context buffer
     pdl_wait();  // the prologue above overlapped the previous kernel (programmatic dependent launch)
+    const int n_work = P.live ? *P.n_live : P.B;  // chunks this launch attends for (rebuilt by an earlier kernel)
 
     if (warp == 4) {
         // ===== TMA producer =====
         if (lane == 0) {
             int g = 0, ci = 0;  // g: global block counter of this CTA, ci: chunk counter
-            for (int b = b_first; b < P.B; b += b_step, ci++) {
+            for (int wi = b_first; wi < n_work; wi += b_step, ci++) {
+                const int b = P.live ? P.live[wi] : wi;
                 ptx::mbar_wait(q_empty, (ci & 1) ^ 1);  // score MMAs of the previous chunk are done with sQ
                 ptx::mbar_expect_tx(q_full, atoms * QATOM_BYTES);
                 for (int a = 0; a < atoms; a++) ptx::tma_load_3d(sQ + a * QATOM_BYTES, &P.q_map, q_full, ch0 + a * 64, 0, b);
@@ -219,7 +224,8 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
             uint64_t a_desc0[2], b_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sQ), 1, 64);
             for (int s = 0; s < 2; s++) a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), 1, 64);
             int g = 0, ci = 0;
-            for (int b = b_first; b < P.B; b += b_step, ci++) {
+            for (int wi = b_first; wi < n_work; wi += b_step, ci++) {
+                const int b = P.live ? P.live[wi] : wi;
                 ptx::mbar_wait(q_full, ci & 1);
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
@@ -252,7 +258,8 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
                 a_desc0[s] = ptx::umma_desc_sw128(ptx::smem_u32(sEnc + s * stage_bytes), ATOM_BYTES >> 4, 64);
             const uint64_t p_desc0 = ptx::umma_desc_sw128(ptx::smem_u32(sP), 1, 64);
             int g = 0, ci = 0;
-            for (int b = b_first; b < P.B; b += b_step, ci++) {
+            for (int wi = b_first; wi < n_work; wi += b_step, ci++) {
+                const int b = P.live ? P.live[wi] : wi;
                 ptx::mbar_wait(&c_empty[ci & 1], ((ci >> 1) & 1) ^ 1);  // epilogue of chunk ci - 2 has drained this buffer
                 const uint32_t tC = tC0 + (ci & 1) * C_BUF;
                 for (int j = 0; j < nblk; j++, g++) {
@@ -317,7 +324,8 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
         };
         int g = 0, ci = 0, b_prev = -1;
         float l_prev[H];
-        for (int b = b_first; b < P.B; b += b_step, ci++) {
+        for (int wi = b_first; wi < n_work; wi += b_step, ci++) {
+                const int b = P.live ? P.live[wi] : wi;
             float m_run[H], l_part[H];
             const uint32_t tC = tC0 + (ci & 1) * C_BUF;
 #pragma unroll
@@ -488,7 +496,7 @@ bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 7
 unsigned long long *g_xa_dbg = nullptr;  // set by the debug hook to collect timestamps
 
 int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16 *ctx,
-                             int B, int S, int D, int H) {
+                             int B, int S, int D, int H, const int *live, const int *n_live) {
     if (B <= 0) return WB_OK;
     WB_ARG(cross_attn_absorbed_supported(D, H) && H * 64 == D,
            "absorbed cross-attention needs head_dim 64, D %% 128 == 0, D <= 768 (D=%d H=%d)", D, H);
@@ -499,6 +507,7 @@ int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16
     WB_CHECK(make_tmap_h16(&P.q_map, qp, (uint64_t)D, (uint64_t)H, (uint64_t)B, (uint64_t)D, (uint64_t)H * D, 16, 3));
     P.ctx = ctx, P.B = B, P.S = S, P.D = D, P.H = H, P.n_blocks = cdiv(S, keys), P.atoms = D / 64;
     P.dbg = g_xa_dbg;
+    P.live = (live && n_live) ? live : nullptr, P.n_live = n_live;
     const size_t smem = cross_attn_absorbed_smem(D);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -152,6 +152,7 @@ struct DecodeAttnDev {
     int H, D, len_const, len_add, splits, smem_len;
     const int *len_dev;
     float *ws;
+    const int *done;
 };
 
 __device__ __forceinline__ uint4 ld_stream(const void *p) {
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x, split = blockIdx.y;
+    if (p.done && p.done[b]) return;  // finished chunk (whisper.mojo:206-207): nothing reads its output any more
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = lane & 7, sub = lane >> 3;
     const int len = p.len_dev ? (*p.len_dev + p.len_add) : p.len_const;
@@ -328,7 +330,7 @@ int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {
     p.q = a.q, p.K = a.K, p.V = a.V, p.out = a.out;
     p.kv_batch_stride = a.kv_batch_stride;
     p.H = a.H, p.D = a.D, p.len_const = a.len_const, p.len_add = a.len_add, p.splits = a.splits;
-    p.len_dev = a.len_dev, p.ws = a.ws;
+    p.len_dev = a.len_dev, p.ws = a.ws, p.done = a.done;
     int chunk = (a.max_len + a.splits - 1) / a.splits;
     p.smem_len = ((chunk + 3) & ~3) + 4;
     size_t smem = (size_t)a.H * p.smem_len * sizeof(float);
@@ -400,8 +402,9 @@ int encoder_attention_ref(cudaStream_t st, const h16 *qkv, h16 *out, int B, int 
 // ---------------------------------------------------------------------------------------------
 __global__ void greedy_init_kernel(GreedyState g, int B, int p0, int p1, int p2, int p3) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) g.scalars[0] = 0, g.scalars[1] = 0, g.scalars[2] = 0;
+    if (i == 0) g.scalars[0] = 0, g.scalars[1] = 0, g.scalars[2] = 0, g.scalars[3] = B;
     if (i >= B) return;
+    if (g.live) g.live[i] = i;
     int *row = g.tokens_out + (size_t)i * g.T_out;
     for (int t = 0; t < g.T_out; t++) row[t] = -1;
     row[0] = p0, row[1] = p1, row[2] = p2, row[3] = p3;
@@ -409,6 +412,43 @@ __global__ void greedy_init_kernel(GreedyState g, int B, int p0, int p1, int p2,
     g.cur_tok[i] = p0;
     g.done[i] = 0;
 }
+// Ordered compaction of the not-done chunk indices: one CTA of 1024 threads, each owning a contiguous run of chunks;
+// an exclusive scan of the per-thread counts places the runs.
+__global__ void __launch_bounds__(1024) greedy_rebuild_live_kernel(GreedyState g, int B) {
+    __shared__ int warp_tot[32];
+    const int tid = threadIdx.x, per = (B + 1023) / 1024, lo = min(B, tid * per), hi = min(B, lo + per);
+    int cnt = 0;
+    for (int i = lo; i < hi; i++) cnt += g.done[i] == 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int w = warp_tot[tid], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (tid >= o) wi += v;
+        }
+        warp_tot[tid] = wi - w;  // exclusive prefix of the warp totals
+        if (tid == 31) g.scalars[3] = wi;
+    }
+    __syncthreads();
+    int pos = warp_tot[tid >> 5] + incl - cnt;
+    for (int i = lo; i < hi; i++)
+        if (g.done[i] == 0) g.live[pos++] = i;
+}
+int greedy_rebuild_live(cudaStream_t st, const GreedyState &g, int B) {
+    WB_ARG(g.live && g.done, "rebuild_live: no live list");
+    greedy_rebuild_live_kernel<<<1, 1024, 0, st>>>(g, B);
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
 int greedy_init(cudaStream_t st, const GreedyState &g, int B, const int *prompt) {
     greedy_init_kernel<<<cdiv(B, 256), 256, 0, st>>>(g, B, prompt[0], prompt[1], prompt[2], prompt[3]);
     WB_LAUNCHED();
@@ -430,6 +470,7 @@ __global__ void greedy_advance_kernel(GreedyState g, int B, int mode, int next_p
             int tok = next[i];
             if (!g.done[i]) {
                 int n = g.out_len[i];
+                if (g.stop_at && n + 1 >= g.stop_at[i]) tok = g.eot;  // forced length (test / bench hook)
                 if (n < g.T_out) {
                     g.tokens_out[(size_t)i * g.T_out + n] = tok;
                     g.out_len[i] = n + 1;
@@ -471,10 +512,11 @@ __global__ void greedy_argmax_advance_kernel(GreedyState g, int B, const float *
             if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
         }
         if (lane == 0) {
-            const int tok = (bi == 0x7fffffff) ? 0 : bi;
+            int tok = (bi == 0x7fffffff) ? 0 : bi;
             next[row] = tok;
             if (!g.done[row]) {
                 const int n = g.out_len[row];
+                if (g.stop_at && n + 1 >= g.stop_at[row]) tok = g.eot;  // forced length (test / bench hook)
                 if (n < g.T_out) {
                     g.tokens_out[(size_t)row * g.T_out + n] = tok;
                     g.out_len[row] = n + 1;

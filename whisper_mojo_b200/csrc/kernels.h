@@ -39,6 +39,7 @@ struct DecodeAttnArgs {
     int max_len;  // upper bound of len (sizes shared memory)
     int splits;
     float *ws;
+    const int *done = nullptr;  // optional [B]: chunks whose flag is set are skipped (their output row keeps its old value)
 };
 int decode_attention(cudaStream_t st, const DecodeAttnArgs &a);
 int decode_attention_splits(int B, int len, int H);
@@ -51,8 +52,9 @@ int encoder_attention_tc(cudaStream_t st, const h16 *qkv, h16 *out, int B, int S
 
 // Decode cross-attention over enc_out itself (cross_attn_tc.cu): q' bf16 [B][H*D], enc bf16 [B][S][D]
 // -> ctx bf16 [B][H*D].  Needs the folded weights below.
+// live / n_live (device, optional): attend only for the chunks live[0 .. *n_live) (finished chunks are skipped).
 int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16 *ctx,
-                             int B, int S, int D, int H);
+                             int B, int S, int D, int H, const int *live = nullptr, const int *n_live = nullptr);
 bool cross_attn_absorbed_supported(int D, int H);
 extern unsigned long long *g_xa_dbg;  // development aid: timestamp buffer for CTA 0 (normally null)
 // Load-time folding (fp32 math, bf16 result):
@@ -69,10 +71,15 @@ struct GreedyState {
     int *out_len;     // [B]
     int *cur_tok;     // [B]
     int *done;        // [B]
-    int *scalars;     // [0]=cur_len, [1]=pos, [2]=n_done
+    int *scalars;     // [0]=cur_len, [1]=pos, [2]=n_done, [3]=n_live
     int T_out, eot, pos_quirk;
+    int *live = nullptr;     // [B] indices of the chunks still decoding, in order (rebuilt by greedy_rebuild_live)
+    int *stop_at = nullptr;  // [B] forced length: the id that brings a chunk's count to stop_at[b] is replaced by EOT
+                             // (INT_MAX = never; a test / bench hook, since EOT never wins with random weights)
 };
 int greedy_init(cudaStream_t st, const GreedyState &g, int B, const int *prompt4_host);
+// live[] = indices b with done[b] == 0 in increasing order, scalars[3] = their count (one CTA: B is at most a few thousand).
+int greedy_rebuild_live(cudaStream_t st, const GreedyState &g, int B);
 // mode 0: prefill advance (feed prompt[next_prompt_idx] next); mode 1: greedy append from `next`.
 int greedy_advance(cudaStream_t st, const GreedyState &g, int B, int mode, int next_prompt_token, const int *next);
 // argmax over the EPI_ARGMAX partials of the logits GEMM + the mode-1 bookkeeping above, in one kernel.

@@ -140,6 +140,7 @@ void model_destroy(Model *m) {
     if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->tr_cache) cache_destroy(m->tr_cache);
     cudaFree(m->tr_mel);
+    cudaFree(m->stop_sched);
     cudaFree(m->stage_in);
     cudaFree(m->stage_out);
     for (void *p : m->owned) cudaFree(p);
@@ -378,6 +379,8 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
     A(&c->out_len, B);
     A(&c->cur_tok, B);
     A(&c->done, B);
+    A(&c->live, B);
+    A(&c->stop_at, B);
     A(&c->scalars, 4 * n_lanes);
     c->lanes.resize(n_lanes);
     for (int i = 0; i < n_lanes && ok; i++) {
@@ -408,6 +411,7 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
         ln.g.out_len = c->out_len + ln.b_off;
         ln.g.cur_tok = c->cur_tok + ln.b_off;
         ln.g.done = c->done + ln.b_off;
+        ln.g.live = c->live + ln.b_off, ln.g.stop_at = c->stop_at + ln.b_off;
         ln.g.scalars = c->scalars + 4 * i;
         ln.g.T_out = T_out, ln.g.eot = m->cfg.eot, ln.g.pos_quirk = m->cfg.pos_quirk;
         ln.counter_bytes = (size_t)(2 * m->L + 2) * chain_counter_ints(ln.B) * sizeof(int);
@@ -450,6 +454,7 @@ int cache_reset(Cache *c) {
     // the reference zero-fills its cache tensors (layers.mojo:30-36)
     WB_CUDA(cudaMemsetAsync(c->self_kv, 0, (size_t)m->L * 2 * c->B * c->T * m->D * sizeof(h16), m->stream));
     for (Lane &ln : c->lanes) WB_CHECK(greedy_init(m->stream, ln.g, ln.B, m->cfg.prompt));
+    WB_CUDA(cudaMemsetAsync(c->stop_at, 0x7f, (size_t)c->B * sizeof(int), m->stream));  // no forced lengths
     c->host_len = 0;
     c->has_cross = false;
     return WB_OK;
@@ -592,6 +597,9 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     // cache-wide segment sizes; this lane's chunks start b_off rows into every segment
     const size_t self_seg = (size_t)c->B * c->T * D, cross_seg = (size_t)c->B * m->S * D;
     const size_t self_off = (size_t)ln.b_off * c->T * D, cross_off = (size_t)ln.b_off * m->S * D;
+    // finished chunks (EOT) drop out of the attention kernels: the self-attention CTA of a done chunk exits at once, the
+    // cross-attention walks the live list (rebuilt every 16 steps next to the host's EOT poll, greedy_loop)
+    const int *skip_done = m->skip_done ? ln.g.done : nullptr, *skip_live = m->skip_done ? ln.g.live : nullptr;
     const bool fused = m->decode_fused && impl == GEMM_IMPL_TC && c->lanes.size() == 1 && D <= 768;
     if (fused && ln.plans.empty()) WB_CHECK(build_chain_plans(c, ln));  // host-only work (tensor maps): capture safe
     if (fused) {
@@ -603,12 +611,14 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
             DecodeAttnArgs a;
             a.q = ln.q, a.K = sk, a.V = sv, a.out = ln.attn, a.kv_batch_stride = (int64_t)c->T * D;
             a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
-            a.splits = 1, a.ws = nullptr;
+            a.splits = 1, a.ws = nullptr, a.done = skip_done;
             WB_CHECK(timed_kernel(m, st, TK_SELF, [&] { return decode_attention(st, a); }));
             WB_CHECK(timed_kernel(m, st, TK_CHAIN_B, [&] { return chain_launch(st, ln.plans[1 + 2 * l]); }));
             if (c->cross_impl == 1) {
                 const h16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
-                WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
+                WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] {
+                    return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H, skip_live, skip_live ? ln.g.scalars + 3 : nullptr);
+                }));
             } else {
                 a.q = ln.q, a.K = c->cross_kv + (size_t)(l * 2) * cross_seg + cross_off, a.V = a.K + cross_seg;
                 a.kv_batch_stride = (int64_t)m->S * D;
@@ -665,7 +675,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         DecodeAttnArgs a;
         a.q = ln.q, a.K = sk, a.V = sv, a.out = ln.attn, a.kv_batch_stride = (int64_t)c->T * D;
         a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
-        a.splits = 1, a.ws = nullptr;
+        a.splits = 1, a.ws = nullptr, a.done = skip_done;
         WB_CHECK(timed_kernel(m, st, TK_SELF, [&] { return decode_attention(st, a); }));
         WB_CHECK(resid_gemm_ln(TK_O, ln.attn, D, d.wo, d.bo, d.ln2_g, d.ln2_b));
         // cross attention over the encoder positions (layers.mojo:463-488)
@@ -676,7 +686,9 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
                 return gemm_run(st, plain_gemm(ln.xn, B, D, d.wqk, HD, d.bqk, EPI_STORE_H16, ln.qp, HD), impl);
             }));
             const h16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
-            WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H); }));
+            WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] {
+                return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H, skip_live, skip_live ? ln.g.scalars + 3 : nullptr);
+            }));
             WB_CHECK(resid_gemm_ln(TK_CO, ln.ctx, HD, d.wov, d.bov, d.ln3_g, d.ln3_b));
         } else {
             WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
@@ -774,6 +786,8 @@ static int greedy_loop(Cache *c) {
     int blk = 0;
     for (int it = 0; it < m->cfg.max_iters; it++) {  // whisper.mojo:205
         if ((it & 15) == 0) {
+            if (m->skip_done && it > 0)  // chunks that finished during the last 16 steps leave the attention kernels
+                for (Lane &ln : c->lanes) WB_CHECK(greedy_rebuild_live(st, ln.g, ln.B));
             WB_CUDA(cudaMemcpyAsync(c->pinned_scalars + 8 * (blk & 1), c->scalars, 4 * n_lanes * sizeof(int),
                                     cudaMemcpyDeviceToHost, st));
             WB_CUDA(cudaEventRecord(c->poll_ev[blk & 1], st));
@@ -917,6 +931,10 @@ static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pc
         }
         if (rc != WB_OK) break;
         c->has_cross = true;
+        if (m->stop_sched) {  // forced lengths of this wave's chunks (chunks past the schedule: none)
+            const int have = std::max(0, std::min(nb, m->stop_sched_n - w0));
+            if (have) cudaMemcpyAsync(c->stop_at, m->stop_sched + w0, (size_t)have * sizeof(int), cudaMemcpyDeviceToDevice, st);
+        }
         cudaEvent_t d0 = m->ev_timed[3 * subs.size() + 2 * wv], d1 = m->ev_timed[3 * subs.size() + 2 * wv + 1];
         cudaEventRecord(d0, st);
         rc = greedy_loop(c);

@@ -69,7 +69,10 @@ struct Model {
         decode_fused = 1,  // 1 = the dense work between two attention kernels runs as one persistent chain kernel
                            // (decode_chain.cu: 4 L + 3 kernels per step instead of 12 L + 4); 0 = round 1's kernel per op
         decode_lanes = 1,  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
-        cross_impl = 1;    // 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (D <= 384)
+        cross_impl = 1,    // 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (D <= 384)
+        skip_done = 1;     // 1 = chunks that produced EOT drop out of the attention kernels (live list rebuilt every 16 steps)
+    int *stop_sched = nullptr;  // device [stop_sched_n]: forced lengths per chunk of a transcribe call (wm_set_stop_lengths)
+    int stop_sched_n = 0;
     Layout lay;
     float *w32 = nullptr;
     bool loaded = false;
@@ -126,6 +129,7 @@ struct Cache {
     h16 *cross_enc = nullptr; // [B][S][D]        (cross_impl 1: enc_out itself, shared by all layers)
     int cross_impl = 0;
     int *tokens_out = nullptr, *out_len = nullptr, *cur_tok = nullptr, *done = nullptr, *scalars = nullptr;
+    int *live = nullptr, *stop_at = nullptr;  // [B]: per lane, the indices still decoding / forced lengths
     std::vector<Lane> lanes;
     std::vector<void *> owned;
     int *pinned_scalars = nullptr;           // two snapshots of the lanes' step scalars (lagged EOT poll)

@@ -179,6 +179,14 @@ class Whisper:
     def set_option(self, key: str, value: int) -> None:
         _lib.check(_lib.load().wm_set_option(self._h, key.encode(), int(value)))
 
+    def set_stop_lengths(self, lens=None) -> None:
+        """Declare per-chunk lengths for later transcribe calls (wm_set_stop_lengths; None clears)."""
+        if lens is None or len(lens) == 0:
+            _lib.check(_lib.load().wm_set_stop_lengths(self._h, None, 0))
+            return
+        a = np.ascontiguousarray(lens, np.int32)
+        _lib.check(_lib.load().wm_set_stop_lengths(self._h, a.ctypes.data_as(c_void_p), a.size))
+
     def stream_ptr(self) -> int:
         """cudaStream_t the model enqueues on (wm_stream)."""
         p = c_void_p(0)

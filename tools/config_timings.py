@@ -27,7 +27,7 @@ m = Whisper(cfg)
 m.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
 lib = _lib.load()
 dev = torch.device("cuda")
-pcm = synth_pcm_gpu(120, cfg.n_samples, dev, 3)
+pcm = synth_pcm_gpu(0, 120, cfg.n_samples, dev, 3)
 mel = torch.empty((120, cfg.n_mels, cfg.n_frames), dtype=torch.float32, device=dev)
 ms = timed(lambda: _lib.check(lib.wm_logmel_dev(m._h, c_void_p(pcm.data_ptr()), 120, c_void_p(mel.data_ptr()))))
 print(f"configs[1] frontend, 1 h of 16 kHz audio (120 chunks) on one GPU: {ms:.3f} ms -> {3600 / (ms * 1e-3):.3e} audio-s/s")
@@ -40,7 +40,7 @@ scfg = WhisperConfig.small_shaped()
 ms_ = Whisper(scfg)
 ms_.load(WeightLoader(data=synth.make_weights(scfg, seed=1)))
 C = 1024
-pcm = synth_pcm_gpu(C, scfg.n_samples, dev, 4)
+pcm = synth_pcm_gpu(0, C, scfg.n_samples, dev, 4)
 ms_.transcribe_pcm_batch(pcm)
 t = timed(lambda: ms_.transcribe_pcm_batch(pcm), reps=2)
 print(f"configs[4] Small-shaped (12 layers, d 768) end to end, {C} chunks on one GPU: {t:.0f} ms -> {C * 30 / (t * 1e-3):.0f} audio-s/s  {ms_.last_timing()}")

@@ -9,7 +9,7 @@ C = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 cfg = WhisperConfig.tiny()
 m = Whisper(cfg)
 m.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
-pcm = synth_pcm_gpu(C, cfg.n_samples, torch.device("cuda"), 1)
+pcm = synth_pcm_gpu(0, C, cfg.n_samples, torch.device("cuda"), 1)
 for _ in range(3):
     m.transcribe_pcm_batch(pcm)
 torch.cuda.synchronize()

@@ -18,7 +18,7 @@ ap.add_argument("--chunks", type=int, default=2048)
 ap.add_argument("--iters", type=int, default=8)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--graph", type=int, default=0)
-ap.add_argument("--lanes", type=int, default=2)
+ap.add_argument("--lanes", type=int, default=1)
 ap.add_argument("--enc-batch", type=int, default=0)
 ap.add_argument("--config", default="tiny", choices=["tiny", "small"])
 ap.add_argument("--cross-impl", type=int, default=-1)
@@ -33,7 +33,7 @@ if a.enc_batch:
 if a.cross_impl >= 0:
     m.set_option("cross_impl", a.cross_impl)
 m.load(WeightLoader(data=synth.make_weights(cfg, seed=0)))
-pcm = synth_pcm_gpu(a.chunks, cfg.n_samples, torch.device("cuda"), 1234)
+pcm = synth_pcm_gpu(0, a.chunks, cfg.n_samples, torch.device("cuda"), 1234)
 for r in range(a.reps):
     torch.cuda.synchronize()
     t = time.time()

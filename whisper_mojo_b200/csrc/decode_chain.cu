@@ -504,9 +504,11 @@ int make_tmap_any_pub(CUtensorMap *map, CUtensorMapDataType dtype, int swizzle_b
 size_t chain_counter_ints(int M) { return (size_t)CHAIN_MAX_PHASES * cdiv(M, BM); }
 
 int chain_split_k(int K) {
-    // ~12 k-blocks of 64 per tile (the ring is 6 deep: two refills), and the slices must tile K exactly
+    // ~6 k-blocks of 64 per tile: one SM streams operands at ~65-75 GB/s whatever the batch (4 x 32 KB in flight per
+    // ring, measured), so a tile's K extent, not its flops, sets the phase time -- 12 k-blocks took 5-6 us, 6 take
+    // ~3.  The slices must tile K exactly, and the factor depends on K only: never on the batch size.
     const int kb = K / BK;
-    int s = std::max(1, (kb + 11) / 12);
+    int s = std::max(1, (kb + 5) / 6);
     while (kb % s) s++;
     return s;
 }

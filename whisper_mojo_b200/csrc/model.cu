@@ -764,7 +764,12 @@ static int greedy_loop(Cache *c) {
         else WB_CHECK(step_all_lanes(c, true, 1, 0));
     }
     const bool graph = m->use_graph && !m->profile_attn;
+    if (c->graph_exec && c->graph_key != (m->decode_fused | (m->skip_done << 1) | ((int)g_pdl << 2))) {
+        cudaGraphExecDestroy(c->graph_exec);  // captured under other launch options: capture again
+        c->graph_exec = nullptr;
+    }
     if (graph && !c->graph_exec) {
+        c->graph_key = m->decode_fused | (m->skip_done << 1) | ((int)g_pdl << 2);
         cudaGraph_t gr = nullptr;
         WB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int64_t l0 = g_launches.load();
@@ -839,11 +844,13 @@ static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pc
 int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
                      int32_t *out_len_dev, const float *in_host) {
     const bool small = m->small_batch > 0 && n > 0 && std::min(n, m->wave_max) <= m->small_batch && m->cross_impl == 1;
-    const int saved_impl = m->cross_impl;
+    const int saved_impl = m->cross_impl, saved_fused = m->decode_fused;
     PdlScope pdl(small || m->pdl);  // this thread's launches only
-    if (small) m->cross_impl = 0;
+    // (kernel-per-op decode for such waves: its launches can overlap through programmatic dependent launch, which the
+    // cooperative chain kernels cannot -- 57 vs 68 ms per clip at batch 1; the two forms produce the same bits)
+    if (small) m->cross_impl = 0, m->decode_fused = 0;
     const int rc = model_transcribe_impl(m, mel_dev, pcm_dev, n, out_tokens_dev, out_len_dev, in_host);
-    m->cross_impl = saved_impl;
+    m->cross_impl = saved_impl, m->decode_fused = saved_fused;
     return rc;
 }
 

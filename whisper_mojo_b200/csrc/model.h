@@ -136,6 +136,7 @@ struct Cache {
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaGraphExec_t graph_exec = nullptr;
     int graph_kernels = 0;  // kernels one replay of graph_exec launches
+    int graph_key = 0;      // launch options graph_exec was captured under (decode_fused, skip_done, pdl)
 };
 
 int model_create(const wm_config *cfg, void *stream, Model **out);

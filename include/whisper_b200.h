@@ -148,8 +148,11 @@ int wm_weight_tensor(wm_model m, int index, void **dev_ptr, int64_t *n_floats);
  * latency-oriented decode: K/V-form cross-attention split over the SMs + programmatic dependent launch; default 0 = off,
  * 8 is a good value for batch-1 use), "decode_split_k" (split-K residual GEMMs + fused residual/LayerNorm in
  * the decode step: 0 = off, 1 = on (default); never a function of the batch size, so a chunk's ids do not depend
- * on how many chunks share its wave), "decode_fused" (1 = persistent chain kernels, 4 L + 3 launches per step
- * (default); 0 = one kernel per op, 12 L + 4), "skip_done" (see wm_set_stop_lengths). */
+ * on how many chunks share its wave), "decode_fused" (1 = persistent chain kernels, 4 L + 3 launches per step;
+ * 0 = one kernel per op, 12 L + 4; 2 (default) = chain kernels for waves of <= 1280 chunks, where the step is latency
+ * bound, kernel per op above -- the two forms produce the same bits), "prefill_impl" (1 (default) = the 4 prompt ids run
+ * as one q_len = 4 forward with the causal block path, whisper.mojo:195-197; 0 = fed one by one through the cached step:
+ * same ids, 3 more forwards), "skip_done" (see wm_set_stop_lengths). */
 int wm_set_option(wm_model m, const char *key, int64_t value);
 
 /* Log-mel frontend (HF WhisperFeatureExtractor via export_weights.py:116): pcm f32 [n_chunks,

@@ -629,3 +629,55 @@ def test_finished_chunks_are_skipped_without_changing_ids(n):
     m.set_stop_lengths(None)
     t2, l2 = m.transcribe_batch(mel)
     assert np.array_equal(t2, free) and np.array_equal(l2, free_len)
+
+
+@pytest.mark.parametrize("shape", ["micro", "tiny", "base_shaped", "small_shaped"])
+def test_prefill_as_one_forward_equals_four_cached_steps(shape):
+    """whisper.mojo:195-197: the reference runs the 4 prompt ids as ONE q_len = 4 forward through the block path with the
+    causal fill (layers.mojo:304-320).  prefill_impl = 1 (default) does the same on the fast path: dense ops on 4 rows
+    per chunk, the causal self-attention, the cross-attention with the prompt rows sharing passes over enc_out (two
+    rows per pass when 2 H <= 16 score columns: micro / tiny / base-shaped; one row per pass on the CTA-pair form:
+    small-shaped), logits of the last row only.  prefill_impl = 0 feeds the ids one by one through the cached step.
+    Every row's arithmetic is the same in both, so the ids must be IDENTICAL -- for the absorbed and the K/V-form cross
+    attention, graph or eager, one or two decode lanes -- and the default must satisfy the oracle rule."""
+    base = {"micro": WhisperConfig.micro(), "tiny": WhisperConfig.tiny(),
+            "base_shaped": WhisperConfig(d_model=512, n_heads=8, n_layers=2),
+            "small_shaped": WhisperConfig.small_shaped()}[shape]
+    cfg = base if shape in ("micro", "tiny") else WhisperConfig(**{**base.__dict__, "max_iters": 10})
+    n = 5 if shape != "small_shaped" else 3
+    mel = synth.make_mel(n, cfg, 23)
+    m1, w = build(cfg, seed=2)
+    t1, l1 = m1.transcribe_batch(mel)
+    m0, _ = build(cfg, seed=2, prefill_impl=0)
+    t0, l0 = m0.transcribe_batch(mel)
+    assert np.array_equal(t0, t1) and np.array_equal(l0, l1), "one-forward prefill changed the ids"
+    for opts in ({"cross_impl": 0}, {"use_graph": 0}, {"decode_fused": 0}):
+        ma, _ = build(cfg, seed=2, **opts)
+        mb, _ = build(cfg, seed=2, prefill_impl=0, **opts)
+        ta, la = ma.transcribe_batch(mel)
+        tb, lb = mb.transcribe_batch(mel)
+        assert np.array_equal(ta, tb) and np.array_equal(la, lb), opts
+    # a chunk alone == the same chunk inside the batch (the prefill's row tiles are 4 x larger than a step's)
+    ts, ls = m1.transcribe_batch(mel[2:3])
+    assert np.array_equal(ts[0], t1[2])
+    if shape in ("micro", "tiny"):
+        om = O.OracleWhisper(cfg, w)
+        for i in range(2):
+            ref, mg = om.greedy(om.encode(mel[i]), margins=True)
+            ok, msg = tokens_agree_up_to_margin(t1[i, :l1[i]], ref, mg, MARGIN_TAU)
+            assert ok, f"chunk {i}: {msg}"
+
+
+def test_prefill_one_forward_with_two_lanes_and_many_row_tiles():
+    """300 micro chunks: the prefill GEMMs see 1200 rows (10 row tiles, ragged last one), two decode lanes prefill on
+    two streams; ids equal the four-cached-steps form."""
+    cfg = WhisperConfig.micro()
+    mel = synth.make_mel(300, cfg, 29)
+    m1, _ = build(cfg)
+    m0, _ = build(cfg, prefill_impl=0)
+    t1, l1 = m1.transcribe_batch(mel)
+    t0, l0 = m0.transcribe_batch(mel)
+    assert np.array_equal(t0, t1) and np.array_equal(l0, l1)
+    m1.set_option("decode_lanes", 2)
+    t2, l2 = m1.transcribe_batch(mel)
+    assert np.array_equal(t2, t1) and np.array_equal(l2, l1)

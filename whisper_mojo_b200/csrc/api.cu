@@ -447,12 +447,16 @@ int wm_set_option(wm_model h, const char *key, int64_t value) {
         }
     }
     else if (!strcmp(key, "decode_fused")) {
-        WB_ARG(value == 0 || value == 1, "decode_fused must be 0 or 1");
+        WB_ARG(value >= 0 && value <= 2, "decode_fused must be 0 (kernel per op), 1 (chain kernels) or 2 (by wave size)");
         if (m->decode_fused != (int)value && m->tr_cache) {
             cache_destroy(m->tr_cache);
             m->tr_cache = nullptr;
         }
         m->decode_fused = (int)value;
+    }
+    else if (!strcmp(key, "prefill_impl")) {
+        WB_ARG(value == 0 || value == 1, "prefill_impl must be 0 (four cached steps) or 1 (one q_len = 4 forward)");
+        m->prefill_impl = (int)value;
     }
     else if (!strcmp(key, "skip_done")) {
         WB_ARG(value == 0 || value == 1, "skip_done must be 0 or 1");

@@ -48,9 +48,12 @@ static constexpr int xa_keys(int atoms) { return atoms <= 6 ? 128 : 64; }
 
 struct CrossAttnParams {
     CUtensorMap enc_map;  // dims (D, S, B), box (64, KEYS, 1)
-    CUtensorMap q_map;    // dims (D, H, B), box (64, 16, 1): rows >= H are zero filled
-    h16 *ctx;   // [B][H*D]
+    CUtensorMap q_map;    // dims (D, q_rows * H, B), box (64, 16, 1): rows >= q_rows * H are zero filled
+    h16 *ctx;   // [B][q_rows][H*D]
     int B, S, D, H, n_blocks, atoms;
+    // Prefill (whisper.mojo:195-197): q_rows query rows per chunk in q' / ctx; this launch attends for the NQ rows
+    // q0 .. q0 + NQ - 1 of every chunk (their heads are the score columns q * H + h).  A decode step: q_rows = 1, q0 = 0.
+    int q_rows, q0;
     // Finished chunks are skipped (whisper.mojo:206-207 `if next_token == 50257: break`, batched): when `live` is set the
     // kernel walks live[0 .. *n_live) -- the indices of the chunks still decoding -- instead of 0 .. B.
     const int *live, *n_live;
@@ -118,7 +121,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
 // variant, whose 72 small UMMAs per 96 KB at ~40-50 clocks each were the limit: tools/ubench_mma.cu).  The score of a
 // key is the sum over all channels, so per block the two CTAs swap their partial scores [128 keys x H] through
 // distributed shared memory, compute the same softmax, and each accumulates the context of its own channels.
-template <int ATOMS, int CL>
+// NQ: query rows per chunk served by one pass over the chunk's encoder output (1 = decode step; 2 = prefill with
+// 2 H <= 16 score columns: the N = 16 UMMAs cost the same whatever number of their columns is in use).
+template <int ATOMS, int CL, int NQ = 1>
 __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
     constexpr int KEYS = xa_keys(ATOMS);
     constexpr int ATOM_BYTES = KEYS * 64 * 2;  // [KEYS x 64 channels] bf16
@@ -149,7 +154,10 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = P.n_blocks, D = P.D;
     pdl_launch_dependents();
-    constexpr int H = ATOMS * CL;     // head_dim = 64, so H = D / 64
+    constexpr int HEADS = ATOMS * CL;  // head_dim = 64, so the model has D / 64 heads
+    constexpr int H = HEADS * NQ;      // score / context columns in use: (query row, head) pairs
+    static_assert(H <= 16, "at most 16 score columns");
+    static_assert(NQ == 1 || CL == 1, "several query rows per pass: single-CTA form only");
     constexpr int n_acc = ATOMS / 2;  // C accumulators of [128 channels x 16 heads]
     static_assert(CL == 1 || KEYS == 128, "the cluster form streams 128-key blocks");
     const uint32_t rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
@@ -204,7 +212,7 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
                 const int b = P.live ? P.live[wi] : wi;
                 ptx::mbar_wait(q_empty, (ci & 1) ^ 1);  // score MMAs of the previous chunk are done with sQ
                 ptx::mbar_expect_tx(q_full, atoms * QATOM_BYTES);
-                for (int a = 0; a < atoms; a++) ptx::tma_load_3d(sQ + a * QATOM_BYTES, &P.q_map, q_full, ch0 + a * 64, 0, b);
+                for (int a = 0; a < atoms; a++) ptx::tma_load_3d(sQ + a * QATOM_BYTES, &P.q_map, q_full, ch0 + a * 64, P.q0 * HEADS, b);
                 for (int j = 0; j < nblk; j++, g++) {
                     const int s = g & 1;
                     for (int a = 0; a < atoms; a++) {
@@ -310,7 +318,8 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
 #pragma unroll
             for (int h = 0; h < H; h++) inv[h] = 1.0f / (s_red[h] + s_red[16 + h] + s_red[32 + h] + s_red[48 + h]);
             ptx::tc_fence_after();
-            h16 *dst = P.ctx + (size_t)b_out * H * D;
+            // column h = (query row q0 + h / HEADS, head h % HEADS): consecutive [D] slices of ctx [B][q_rows][HEADS * D]
+            h16 *dst = P.ctx + ((size_t)b_out * P.q_rows + P.q0) * HEADS * D;
             for (int m = 0; m < n_acc; m++) {
                 uint32_t cv[16];
                 tmem_ld_32x32b_x16(tC + 16 * m + lane_addr, cv);
@@ -465,9 +474,9 @@ __device__ __forceinline__ void xa_body(const CrossAttnParams &P) {
     if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-template <int ATOMS>
+template <int ATOMS, int NQ = 1>
 __global__ void __launch_bounds__(XA_THREADS, 1) cross_attn_absorbed_kernel(const __grid_constant__ CrossAttnParams P) {
-    xa_body<ATOMS, 1>(P);
+    xa_body<ATOMS, 1, NQ>(P);
 }
 template <int ATOMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XA_THREADS, 1)
@@ -496,16 +505,18 @@ bool cross_attn_absorbed_supported(int D, int H) { return D % 128 == 0 && D <= 7
 unsigned long long *g_xa_dbg = nullptr;  // set by the debug hook to collect timestamps
 
 int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16 *ctx,
-                             int B, int S, int D, int H, const int *live, const int *n_live) {
+                             int B, int S, int D, int H, const int *live, const int *n_live, int q_rows) {
     if (B <= 0) return WB_OK;
     WB_ARG(cross_attn_absorbed_supported(D, H) && H * 64 == D,
            "absorbed cross-attention needs head_dim 64, D %% 128 == 0, D <= 768 (D=%d H=%d)", D, H);
+    WB_ARG(q_rows >= 1 && q_rows <= 4, "absorbed cross-attention: q_rows=%d", q_rows);
     CrossAttnParams P;
     const bool pair = xa_use_pair(D / 64);
     const int keys = xa_keys(pair ? D / 128 : D / 64);
     WB_CHECK(make_tmap_h16(&P.enc_map, enc, (uint64_t)D, (uint64_t)S, (uint64_t)B, (uint64_t)D, (uint64_t)S * D, keys, 3));
-    WB_CHECK(make_tmap_h16(&P.q_map, qp, (uint64_t)D, (uint64_t)H, (uint64_t)B, (uint64_t)D, (uint64_t)H * D, 16, 3));
+    WB_CHECK(make_tmap_h16(&P.q_map, qp, (uint64_t)D, (uint64_t)q_rows * H, (uint64_t)B, (uint64_t)D, (uint64_t)q_rows * H * D, 16, 3));
     P.ctx = ctx, P.B = B, P.S = S, P.D = D, P.H = H, P.n_blocks = cdiv(S, keys), P.atoms = D / 64;
+    P.q_rows = q_rows, P.q0 = 0;
     P.dbg = g_xa_dbg;
     P.live = (live && n_live) ? live : nullptr, P.n_live = n_live;
     const size_t smem = cross_attn_absorbed_smem(D);
@@ -519,15 +530,36 @@ int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16
         WB_LAUNCHED();
         return WB_OK;
     };
-    if (pair) return P.atoms == 8 ? launch(cross_attn_absorbed_pair_kernel<4>, 6) : launch(cross_attn_absorbed_pair_kernel<6>, 7);
-    switch (P.atoms) {
-        case 2: return launch(cross_attn_absorbed_kernel<2>, 0);
-        case 4: return launch(cross_attn_absorbed_kernel<4>, 1);
-        case 6: return launch(cross_attn_absorbed_kernel<6>, 2);
-        case 8: return launch(cross_attn_absorbed_kernel<8>, 3);
-        case 10: return launch(cross_attn_absorbed_kernel<10>, 4);
-        default: return launch(cross_attn_absorbed_kernel<12>, 5);
+    auto one_pass = [&]() -> int {
+        if (pair) return P.atoms == 8 ? launch(cross_attn_absorbed_pair_kernel<4>, 6) : launch(cross_attn_absorbed_pair_kernel<6>, 7);
+        switch (P.atoms) {
+            case 2: return launch(cross_attn_absorbed_kernel<2>, 0);
+            case 4: return launch(cross_attn_absorbed_kernel<4>, 1);
+            case 6: return launch(cross_attn_absorbed_kernel<6>, 2);
+            case 8: return launch(cross_attn_absorbed_kernel<8>, 3);
+            case 10: return launch(cross_attn_absorbed_kernel<10>, 4);
+            default: return launch(cross_attn_absorbed_kernel<12>, 5);
+        }
+    };
+    if (q_rows == 1) return one_pass();
+    // Prefill: the q_rows query rows of a chunk attend over the same encoder output.  With 2 H <= 16 two rows share
+    // one pass (their heads are 2 H of the 16 score columns the N = 16 UMMAs compute anyway), so the 4-id prompt
+    // costs two reads of enc_out instead of four; otherwise one pass per row.
+    const bool two = !pair && 2 * H <= 16 && q_rows % 2 == 0;
+    for (int q0 = 0; q0 < q_rows; q0 += two ? 2 : 1) {
+        P.q0 = q0;
+        if (!two) {
+            WB_CHECK(one_pass());
+            continue;
+        }
+        switch (P.atoms) {
+            case 2: WB_CHECK(launch(cross_attn_absorbed_kernel<2, 2>, 8)); break;
+            case 4: WB_CHECK(launch(cross_attn_absorbed_kernel<4, 2>, 9)); break;
+            case 6: WB_CHECK(launch(cross_attn_absorbed_kernel<6, 2>, 10)); break;
+            default: WB_CHECK(launch(cross_attn_absorbed_kernel<8, 2>, 11)); break;
+        }
     }
+    return WB_OK;
 }
 
 }  // namespace wb

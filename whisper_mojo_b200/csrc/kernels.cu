@@ -28,6 +28,10 @@ __global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x
                                                       const float *__restrict__ pos_emb,
                                                       const int *__restrict__ cur_tok, const int *__restrict__ pos_dev,
                                                       int vocab, int n_pos, float *__restrict__ x_out,
+                                                      // LN_EMBED, prefill (q_len > 1): row r holds prompt token r % q_len at
+                                                      // position r % q_len; *set_len = q_len - 1 (the bookkeeping kernel
+                                                      // after the logits adds the last 1)
+                                                      int q_len, int4 prompt, int *__restrict__ set_len,
                                                       // LN_RESID only:
                                                       const float *__restrict__ part, int n_split,
                                                       long long split_stride, const float *__restrict__ bias) {
@@ -59,9 +63,16 @@ __global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x
             }
         if (!gamma) return;
     } else if (EMBED == LN_EMBED) {
-        int tok = cur_tok[row];
+        int tok, pos;
+        if (q_len > 1) {  // whisper.mojo:195-197: the prompt ids at positions 0 .. q_len-1, every chunk alike
+            pos = row % q_len;
+            tok = pos == 0 ? prompt.x : (pos == 1 ? prompt.y : (pos == 2 ? prompt.z : prompt.w));
+            if (row == 0 && lane == 0 && set_len) *set_len = q_len - 1;
+        } else {
+            tok = cur_tok[row];
+            pos = *pos_dev;
+        }
         tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
-        int pos = *pos_dev;
         pos = pos < 0 ? 0 : (pos >= n_pos ? n_pos - 1 : pos);
         const float4 *te = reinterpret_cast<const float4 *>(tok_emb + (size_t)tok * D);
         const float4 *pe = reinterpret_cast<const float4 *>(pos_emb + (size_t)pos * D);
@@ -112,7 +123,7 @@ int ln_h16(cudaStream_t st, const float *x, const float *gamma, const float *bet
     WB_ARG(D % 128 == 0 && D <= 1024, "ln_h16: D=%d must be a multiple of 128 and <= 1024", D);
     if (rows <= 0) return WB_OK;
     WB_CUDA(launch_pdl(ln_h16_kernel<LN_PLAIN>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, gamma, beta, rows, D, out_h16,
-                       out_f32, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, 0, nullptr));
+                       out_f32, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, 1, make_int4(0, 0, 0, 0), nullptr, nullptr, 0, 0, nullptr));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -123,7 +134,7 @@ int resid_ln(cudaStream_t st, float *x, const float *part, int n_split, const fl
     WB_ARG(x && part && n_split >= 1 && (!gamma || (beta && out_h16)), "resid_ln: bad arguments");
     if (rows <= 0) return WB_OK;
     WB_CUDA(launch_pdl(ln_h16_kernel<LN_RESID>, dim3(cdiv(rows, 8)), dim3(256), 0, st, nullptr, gamma, beta, rows, D, out_h16,
-                       nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, x, part, n_split, (long long)rows * D, bias));
+                       nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, x, 1, make_int4(0, 0, 0, 0), nullptr, part, n_split, (long long)rows * D, bias));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -134,7 +145,43 @@ int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const 
     WB_ARG(D % 128 == 0 && D <= 1024, "embed_ln: D=%d must be a multiple of 128 and <= 1024", D);
     if (B <= 0) return WB_OK;
     WB_CUDA(launch_pdl(ln_h16_kernel<LN_EMBED>, dim3(cdiv(B, 8)), dim3(256), 0, st, nullptr, gamma, beta, B, D, xn, nullptr,
-                       tok_emb, pos_emb, cur_tok, pos_dev, vocab, n_pos, x, nullptr, 0, 0, nullptr));
+                       tok_emb, pos_emb, cur_tok, pos_dev, vocab, n_pos, x, 1, make_int4(0, 0, 0, 0), nullptr, nullptr, 0, 0, nullptr));
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+int embed_ln_prefill(cudaStream_t st, const float *tok_emb, const float *pos_emb, const int *prompt4_host, int q_len, int B,
+                     int D, int vocab, int n_pos, const float *gamma, const float *beta, float *x, h16 *xn, int *set_len) {
+    WB_ARG(D % 128 == 0 && D <= 1024, "embed_ln_prefill: D=%d must be a multiple of 128 and <= 1024", D);
+    WB_ARG(q_len >= 2 && q_len <= 4, "embed_ln_prefill: q_len=%d (the reference's prompt has 4 ids)", q_len);
+    if (B <= 0) return WB_OK;
+    const int4 pr = make_int4(prompt4_host[0], prompt4_host[1], prompt4_host[2], prompt4_host[3]);
+    WB_CUDA(launch_pdl(ln_h16_kernel<LN_EMBED>, dim3(cdiv(B * q_len, 8)), dim3(256), 0, st, nullptr, gamma, beta, B * q_len, D, xn,
+                       nullptr, tok_emb, pos_emb, nullptr, nullptr, vocab, n_pos, x, q_len, pr, set_len, nullptr, 0, 0, nullptr));
+    WB_LAUNCHED();
+    return WB_OK;
+}
+
+// k / v rows of a q_len-token forward, [B * q_len][D] each (row b * q_len + p), into rows 0 .. q_len-1 of the self K/V
+// cache (layers.mojo:131-143 with start_pos = 0): one 16-byte piece per thread.
+__global__ void kv_scatter_kernel(const h16 *__restrict__ k, const h16 *__restrict__ v, h16 *__restrict__ Kc,
+                                  h16 *__restrict__ Vc, int rows, int q_len, int D, long long kv_batch_stride) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int per_row = D >> 3;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * per_row) return;
+    const int r = (int)(i / per_row), c = (int)(i - (long long)r * per_row);
+    const long long dst = (long long)(r / q_len) * kv_batch_stride + (long long)(r % q_len) * D + c * 8;
+    *reinterpret_cast<uint4 *>(Kc + dst) = *reinterpret_cast<const uint4 *>(k + (size_t)r * D + c * 8);
+    *reinterpret_cast<uint4 *>(Vc + dst) = *reinterpret_cast<const uint4 *>(v + (size_t)r * D + c * 8);
+}
+int kv_scatter(cudaStream_t st, const h16 *k, const h16 *v, h16 *Kc, h16 *Vc, int B, int q_len, int D, int64_t kv_batch_stride) {
+    WB_ARG(D % 8 == 0 && q_len >= 1, "kv_scatter: bad shape");
+    if (B <= 0) return WB_OK;
+    const long long n = (long long)B * q_len * (D >> 3);
+    WB_CUDA(launch_pdl(kv_scatter_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, k, v, Kc, Vc, B * q_len, q_len, D,
+                       (long long)kv_batch_stride));
     WB_LAUNCHED();
     return WB_OK;
 }
@@ -150,6 +197,7 @@ struct DecodeAttnDev {
     h16 *out;
     long long kv_batch_stride;
     int H, D, len_const, len_add, splits, smem_len;
+    int q_len;  // > 1: grid row vb is query vb % q_len of chunk vb / q_len; without len_const it attends keys 0 .. vb % q_len
     const int *len_dev;
     float *ws;
     const int *done;
@@ -167,11 +215,16 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
     extern __shared__ float s_scores[];  // [H][smem_len]
     pdl_launch_dependents();
     pdl_wait();
+    // b: row of q / out / ws; kb: the chunk whose K / V it attends over.  q_len > 1 is the causal block path of the
+    // reference (layers.mojo:304-320: keys j > i are filled with -1e10, i.e. they get weight exp(-1e10 - max) = 0
+    // exactly) done as q_len independent single-query problems of lengths 1 .. q_len -- the arithmetic of a row is the
+    // one a cached single-token step at that position runs, bit for bit.
     const int b = blockIdx.x, split = blockIdx.y;
-    if (p.done && p.done[b]) return;  // finished chunk (whisper.mojo:206-207): nothing reads its output any more
+    const int kb = p.q_len > 1 ? b / p.q_len : b;
+    if (p.done && p.done[kb]) return;  // finished chunk (whisper.mojo:206-207): nothing reads its output any more
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = lane & 7, sub = lane >> 3;
-    const int len = p.len_dev ? (*p.len_dev + p.len_add) : p.len_const;
+    const int len = p.len_dev ? (*p.len_dev + p.len_add) : (p.len_const > 0 ? p.len_const : b % p.q_len + 1);
     int chunk = (len + p.splits - 1) / p.splits;
     chunk = (chunk + 3) & ~3;
     const int j0 = split * chunk;
@@ -182,8 +235,8 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
     float qf[8];
     h8_to_float(*reinterpret_cast<const uint4 *>(p.q + (size_t)b * p.D + h * 64 + c * 8), qf);
     const float scale = 0.125f;  // 1/sqrt(head_dim), head_dim = 64 (layers.mojo:184)
-    const h16 *Kb = p.K + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
-    const h16 *Vb = p.V + (size_t)b * p.kv_batch_stride + h * 64 + c * 8;
+    const h16 *Kb = p.K + (size_t)kb * p.kv_batch_stride + h * 64 + c * 8;
+    const h16 *Vb = p.V + (size_t)kb * p.kv_batch_stride + h * 64 + c * 8;
 
     // phase 1: scores
     float m = -1e10f;  // layers.mojo:188
@@ -331,6 +384,9 @@ int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {
     p.kv_batch_stride = a.kv_batch_stride;
     p.H = a.H, p.D = a.D, p.len_const = a.len_const, p.len_add = a.len_add, p.splits = a.splits;
     p.len_dev = a.len_dev, p.ws = a.ws, p.done = a.done;
+    p.q_len = a.q_len < 1 ? 1 : a.q_len;
+    WB_ARG(p.q_len == 1 || (!a.len_dev && a.B % p.q_len == 0), "decode_attention: q_len=%d needs B %% q_len == 0 and no device length", p.q_len);
+    WB_ARG(a.len_dev || a.len_const > 0 || p.q_len > 1, "decode_attention: no key length");
     int chunk = (a.max_len + a.splits - 1) / a.splits;
     p.smem_len = ((chunk + 3) & ~3) + 4;
     size_t smem = (size_t)a.H * p.smem_len * sizeof(float);

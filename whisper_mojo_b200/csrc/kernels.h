@@ -22,6 +22,14 @@ int embed_ln(cudaStream_t st, const float *tok_emb, const float *pos_emb, const 
              int B, int D, int vocab, int n_pos, const float *gamma, const float *beta, float *x,
              h16 *xn);
 
+// Prefill (whisper.mojo:195-197): rows b * q_len + p = token_emb[prompt[p]] + pos_emb[p] for every chunk b, then the
+// same LayerNorm; *set_len = q_len - 1 (cur_len once the bookkeeping kernel after the logits has added the last 1).
+int embed_ln_prefill(cudaStream_t st, const float *tok_emb, const float *pos_emb, const int *prompt4_host, int q_len, int B,
+                     int D, int vocab, int n_pos, const float *gamma, const float *beta, float *x, h16 *xn, int *set_len);
+// k / v [B * q_len][D] of a q_len-token forward -> rows 0 .. q_len-1 of the chunks' self K/V cache (chunk stride
+// kv_batch_stride elements).
+int kv_scatter(cudaStream_t st, const h16 *k, const h16 *v, h16 *Kc, h16 *Vc, int B, int q_len, int D, int64_t kv_batch_stride);
+
 // Single-query attention for one decode step (layers.mojo:186-272), batched over chunks and heads.
 //   q   bf16 [B][D]                         (head h = columns h*64 .. h*64+63)
 //   K,V bf16 [B][rows][D], chunk stride `kv_batch_stride` elements
@@ -40,6 +48,9 @@ struct DecodeAttnArgs {
     int splits;
     float *ws;
     const int *done = nullptr;  // optional [B]: chunks whose flag is set are skipped (their output row keeps its old value)
+    // q_len > 1 (prefill, layers.mojo:273-342 with the causal fill :304-320): B counts query ROWS, row vb = query
+    // vb % q_len of chunk vb / q_len; with len_const == 0 and no len_dev it attends over keys 0 .. vb % q_len.
+    int q_len = 1;
 };
 int decode_attention(cudaStream_t st, const DecodeAttnArgs &a);
 int decode_attention_splits(int B, int len, int H);
@@ -53,8 +64,9 @@ int encoder_attention_tc(cudaStream_t st, const h16 *qkv, h16 *out, int B, int S
 // Decode cross-attention over enc_out itself (cross_attn_tc.cu): q' bf16 [B][H*D], enc bf16 [B][S][D]
 // -> ctx bf16 [B][H*D].  Needs the folded weights below.
 // live / n_live (device, optional): attend only for the chunks live[0 .. *n_live) (finished chunks are skipped).
+// q_rows > 1 (prefill): q' and ctx hold q_rows rows per chunk, [B][q_rows][H*D]; every row attends over the chunk's enc.
 int cross_attention_absorbed(cudaStream_t st, const h16 *qp, const h16 *enc, h16 *ctx,
-                             int B, int S, int D, int H, const int *live = nullptr, const int *n_live = nullptr);
+                             int B, int S, int D, int H, const int *live = nullptr, const int *n_live = nullptr, int q_rows = 1);
 bool cross_attn_absorbed_supported(int D, int H);
 extern unsigned long long *g_xa_dbg;  // development aid: timestamp buffer for CTA 0 (normally null)
 // Load-time folding (fp32 math, bf16 result):

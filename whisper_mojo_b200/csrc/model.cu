@@ -388,23 +388,28 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
         ln.b_off = (int)((int64_t)B * i / n_lanes);
         ln.B = (int)((int64_t)B * (i + 1) / n_lanes) - ln.b_off;
         ln.cross_splits = decode_attention_splits(ln.B, m->S, m->H);
-        A(&ln.x, ln.B * D);
-        A(&ln.xn, ln.B * D);
-        A(&ln.q, ln.B * D);
-        A(&ln.attn, ln.B * D);
-        A(&ln.h, (size_t)ln.B * m->F);
+        // the row buffers hold PREFILL_LEN rows per chunk: the prompt runs as ONE q_len = 4 forward (whisper.mojo:195-197),
+        // a decode step uses the first B rows
+        const size_t R = (size_t)ln.B * PREFILL_LEN;
+        A(&ln.x, R * D);
+        A(&ln.xn, R * D);
+        A(&ln.q, R * D);
+        A(&ln.pf_k, R * D);
+        A(&ln.pf_v, R * D);
+        A(&ln.attn, R * D);
+        A(&ln.h, R * m->F);
         A(&ln.part_val, (size_t)ln.B * slots);
         A(&ln.part_idx, (size_t)ln.B * slots);
         A(&ln.next, ln.B);
-        A(&ln.attn_ws, (size_t)ln.B * ln.cross_splits * m->H * 66);
+        A(&ln.attn_ws, R * ln.cross_splits * m->H * 66);
         // split-K partial products of the residual GEMMs: round 1's form uses up to 4 slices, the chain kernel
         // chain_split_k(K) of them for K = D (o), H*D or D (cross-o) and F (fc2)
         ln.part_splits = std::max({4, chain_split_k((int)D), chain_split_k(c->cross_impl == 1 ? m->H * (int)D : (int)D),
                                    chain_split_k(m->F)});
-        A(&ln.part, (size_t)ln.part_splits * ln.B * D);
+        A(&ln.part, (size_t)ln.part_splits * R * D);
         if (c->cross_impl == 1) {
-            A(&ln.qp, (size_t)ln.B * m->H * D);
-            A(&ln.ctx, (size_t)ln.B * m->H * D);
+            A(&ln.qp, R * m->H * D);
+            A(&ln.ctx, R * m->H * D);
         }
         if (want_logits || m->gemm_impl == GEMM_IMPL_REF) A(&ln.logits, (size_t)ln.B * m->V);
         ln.g.tokens_out = c->tokens_out + (size_t)ln.b_off * T_out;
@@ -589,9 +594,17 @@ static int timed_kernel(Model *m, cudaStream_t st, int category, Fn launch) {
 
 // One decoder forward with q_len = 1 for every chunk of the cache (whisper.mojo:130-167,
 // layers.mojo:435-519 with is_decoder = True).  Token / position / cur_len come from device memory.
-int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits, bool advance) {
+// q_len = 1: one cached decode step for the lane's chunks (layers.mojo:186-272 path).  q_len = PREFILL_LEN: the
+// reference's prefill, `decoder.forward(prompt ids, enc, cache, 0)` (whisper.mojo:195-197), as ONE forward over
+// R = q_len * B rows (row b * q_len + p = prompt position p of chunk b): the dense ops run on R rows, the self
+// attention is the causal block path (layers.mojo:273-342, mask :304-320) and only the last position's logits are
+// computed (whisper.mojo:159-166).  Every row's arithmetic is the one the cached single-token step at that position
+// runs (same GEMM K order, same attention kernels), so the ids do not depend on which form ran -- tested.
+int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits, bool advance, int q_len) {
     Model *m = c->m;
     const int B = ln.B, D = m->D, impl = m->gemm_impl;
+    const int R = B * q_len;  // rows of the dense ops
+    WB_ARG(q_len == 1 || (q_len == PREFILL_LEN && with_logits && c->host_len == 0), "decode_step: bad prefill call");
     const float *W = m->w32;
     int *cur_len = ln.g.scalars, *pos = ln.g.scalars + 1;
     // cache-wide segment sizes; this lane's chunks start b_off rows into every segment
@@ -600,7 +613,11 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     // finished chunks (EOT) drop out of the attention kernels: the self-attention CTA of a done chunk exits at once, the
     // cross-attention walks the live list (rebuilt every 16 steps next to the host's EOT poll, greedy_loop)
     const int *skip_done = m->skip_done ? ln.g.done : nullptr, *skip_live = m->skip_done ? ln.g.live : nullptr;
-    const bool fused = m->decode_fused && impl == GEMM_IMPL_TC && c->lanes.size() == 1 && D <= 768;
+    // decode_fused = 2: by wave size.  The chain kernels win while the step is latency bound; from ~1.3 k chunks on the
+    // phases are throughput bound and the CTA-pair GEMM kernels of the kernel-per-op form are ahead (B200, Tiny:
+    // 1024 chunks 249.8 vs 252.8 ms, 1536: 349.8 vs 342.8, 2048: 445 vs 434; tools/fused_ab.py).  Same bits either way.
+    const bool want_fused = m->decode_fused == 1 || (m->decode_fused == 2 && B <= FUSED_MAX_WAVE);
+    const bool fused = q_len == 1 && want_fused && impl == GEMM_IMPL_TC && c->lanes.size() == 1 && D <= 768;
     if (fused && ln.plans.empty()) WB_CHECK(build_chain_plans(c, ln));  // host-only work (tensor maps): capture safe
     if (fused) {
         // 4 L + 3 kernels: chain | self-attn | chain | cross-attn | chain | ... | logits+argmax | argmax reduce
@@ -631,6 +648,9 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         }
     } else {
     WB_CHECK(timed_kernel(m, st, TK_LN, [&] {
+        if (q_len > 1)  // rows b * q_len + p = prompt id p at position p; cur_len becomes q_len - 1 (+ 1 after the logits)
+            return embed_ln_prefill(st, W + m->lay.tok_emb, W + m->lay.dec_pos, m->cfg.prompt, q_len, B, D, m->V, m->T,
+                                    m->dec[0].ln1_g, m->dec[0].ln1_b, ln.x, ln.xn, cur_len);
         return embed_ln(st, W + m->lay.tok_emb, W + m->lay.dec_pos, ln.g.cur_tok, pos, B, D, m->V, m->T, m->dec[0].ln1_g,
                         m->dec[0].ln1_b, ln.x, ln.xn);
     }));
@@ -647,16 +667,16 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         // low-margin steps) do not depend on how many other chunks share the wave.
         if (impl == GEMM_IMPL_TC && ln.part && m->decode_split_k >= 1) {
             const int split = chain_split_k(K);
-            GemmDesc gd = plain_gemm(A, B, K, Wt, D, nullptr, EPI_STORE_F32, ln.part, D);
+            GemmDesc gd = plain_gemm(A, R, K, Wt, D, nullptr, EPI_STORE_F32, ln.part, D);
             gd.split_k = split;
             WB_CHECK(timed_kernel(m, st, cat, [&] { return gemm_run(st, gd, impl); }));
-            return timed_kernel(m, st, TK_LN, [&] { return resid_ln(st, ln.x, ln.part, split, bias, g, bb, B, D, ln.xn); });
+            return timed_kernel(m, st, TK_LN, [&] { return resid_ln(st, ln.x, ln.part, split, bias, g, bb, R, D, ln.xn); });
         }
         WB_CHECK(timed_kernel(m, st, cat, [&] {
-            return gemm_run(st, plain_gemm(A, B, K, Wt, D, bias, EPI_RESID_F32, ln.x, D), impl);
+            return gemm_run(st, plain_gemm(A, R, K, Wt, D, bias, EPI_RESID_F32, ln.x, D), impl);
         }));
         if (!g) return WB_OK;
-        return timed_kernel(m, st, TK_LN, [&] { return ln_h16(st, ln.x, g, bb, B, D, ln.xn, nullptr); });
+        return timed_kernel(m, st, TK_LN, [&] { return ln_h16(st, ln.x, g, bb, R, D, ln.xn, nullptr); });
     };
     for (int l = 0; l < m->L; l++) {
         const LayerDev &d = m->dec[l];
@@ -665,17 +685,25 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         h16 *cv = ck ? ck + cross_seg : nullptr;
         // (xn = LN1(x) was produced by embed_ln / by the previous layer's fc2 step)
         {  // q, k, v projections; k / v rows land in the cache at position cur_len (layers.mojo:131-143)
-            GemmDesc g = plain_gemm(ln.xn, B, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_H16, ln.q, D);
+            GemmDesc g = plain_gemm(ln.xn, R, D, d.wqkv, 3 * D, d.bqkv, EPI_STORE_H16, ln.q, D);
             g.n_seg_ptrs = 3, g.seg_cols = D;
-            g.out[1] = sk, g.out_ld[1] = (int64_t)c->T * D, g.dyn_mult[1] = D;
-            g.out[2] = sv, g.out_ld[2] = (int64_t)c->T * D, g.dyn_mult[2] = D;
-            g.dyn_off = cur_len;
+            if (q_len == 1) {
+                g.out[1] = sk, g.out_ld[1] = (int64_t)c->T * D, g.dyn_mult[1] = D;
+                g.out[2] = sv, g.out_ld[2] = (int64_t)c->T * D, g.dyn_mult[2] = D;
+                g.dyn_off = cur_len;
+            } else {  // prefill: k / v rows [R][D], then into cache rows 0 .. q_len-1 of their chunks
+                g.out[1] = ln.pf_k, g.out_ld[1] = D;
+                g.out[2] = ln.pf_v, g.out_ld[2] = D;
+            }
             WB_CHECK(timed_kernel(m, st, TK_QKV, [&] { return gemm_run(st, g, impl); }));
+            if (q_len > 1)
+                WB_CHECK(timed_kernel(m, st, TK_MISC, [&] { return kv_scatter(st, ln.pf_k, ln.pf_v, sk, sv, B, q_len, D, (int64_t)c->T * D); }));
         }
         DecodeAttnArgs a;
         a.q = ln.q, a.K = sk, a.V = sv, a.out = ln.attn, a.kv_batch_stride = (int64_t)c->T * D;
-        a.B = B, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
+        a.B = R, a.H = m->H, a.D = D, a.len_const = 0, a.len_dev = cur_len, a.len_add = 1, a.max_len = c->T;
         a.splits = 1, a.ws = nullptr, a.done = skip_done;
+        if (q_len > 1) a.len_dev = nullptr, a.len_add = 0, a.q_len = q_len, a.done = nullptr;  // causal: row p sees keys 0 .. p
         WB_CHECK(timed_kernel(m, st, TK_SELF, [&] { return decode_attention(st, a); }));
         WB_CHECK(resid_gemm_ln(TK_O, ln.attn, D, d.wo, d.bo, d.ln2_g, d.ln2_b));
         // cross attention over the encoder positions (layers.mojo:463-488)
@@ -683,18 +711,19 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
             // absorbed form: q' = (Wk_h^T Wq_h) x + ..., attend over enc_out, out = (Wo Wv_h) ctx_h + ...
             const int HD = m->H * D;
             WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
-                return gemm_run(st, plain_gemm(ln.xn, B, D, d.wqk, HD, d.bqk, EPI_STORE_H16, ln.qp, HD), impl);
+                return gemm_run(st, plain_gemm(ln.xn, R, D, d.wqk, HD, d.bqk, EPI_STORE_H16, ln.qp, HD), impl);
             }));
             const h16 *enc = c->cross_enc + (size_t)ln.b_off * m->S * D;
             WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] {
+                if (q_len > 1) return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H, nullptr, nullptr, q_len);
                 return cross_attention_absorbed(st, ln.qp, enc, ln.ctx, B, m->S, D, m->H, skip_live, skip_live ? ln.g.scalars + 3 : nullptr);
             }));
             WB_CHECK(resid_gemm_ln(TK_CO, ln.ctx, HD, d.wov, d.bov, d.ln3_g, d.ln3_b));
         } else {
             WB_CHECK(timed_kernel(m, st, TK_CQ, [&] {
-                return gemm_run(st, plain_gemm(ln.xn, B, D, d.cwq, D, d.cbq, EPI_STORE_H16, ln.q, D), impl);
+                return gemm_run(st, plain_gemm(ln.xn, R, D, d.cwq, D, d.cbq, EPI_STORE_H16, ln.q, D), impl);
             }));
-            a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;
+            a.K = ck, a.V = cv, a.kv_batch_stride = (int64_t)m->S * D;  // (q_len > 1: every row of a chunk sees all S keys)
             a.len_const = m->S, a.len_dev = nullptr, a.len_add = 0, a.max_len = m->S;
             a.splits = ln.cross_splits, a.ws = ln.attn_ws;
             WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return decode_attention(st, a); }));
@@ -703,7 +732,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
         // MLP (layers.mojo:490-517); the LayerNorm after fc2 is the next layer's attn_ln, or the decoder's ln_post
         // in front of the logits (whisper.mojo:156-158), or none on a prefill step
         WB_CHECK(timed_kernel(m, st, TK_FC1, [&] {
-            return gemm_run(st, plain_gemm(ln.xn, B, D, d.w1, m->F, d.b1, EPI_GELU_H16, ln.h, m->F), impl);
+            return gemm_run(st, plain_gemm(ln.xn, R, D, d.w1, m->F, d.b1, EPI_GELU_H16, ln.h, m->F), impl);
         }));
         const bool last = l + 1 == m->L;
         const float *ng = last ? (with_logits ? W + m->lay.dec_ln_w : nullptr) : m->dec[l + 1].ln1_g;
@@ -712,7 +741,9 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     }
     }  // !fused
     if (with_logits) {  // whisper.mojo:156-166 + argmax :198,219
-        GemmDesc g = plain_gemm(ln.xn, B, D, m->tok_emb_h16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
+        // prefill: only the last position's logits (whisper.mojo:159-166 slices row q_len - 1): rows q_len - 1, 2 q_len - 1, ...
+        GemmDesc g = plain_gemm(ln.xn + (size_t)(q_len - 1) * D, B, D, m->tok_emb_h16, m->V, nullptr, EPI_ARGMAX, nullptr, 0);
+        g.lda = q_len * D;
         g.part_val = ln.part_val, g.part_idx = ln.part_idx;
         g.logits = (store_logits || impl == GEMM_IMPL_REF) ? ln.logits : nullptr;
         WB_ARG(!(store_logits || impl == GEMM_IMPL_REF) || ln.logits, "decode_step: cache has no logits buffer");
@@ -731,6 +762,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
 // ---------------------------------------------------------------------------------------------
 // One greedy step for every lane.  With two lanes the second one runs on stream2 between a fork and
 // a join event, so the same code serves eager execution and stream capture into one graph.
+// mode 0: prompt step (feed next_prompt_token next), 1: greedy step, 2: the whole prompt as one q_len = 4 forward
 static int step_all_lanes(Cache *c, bool with_logits, int mode, int next_prompt_token) {
     Model *m = c->m;
     const bool two = c->lanes.size() > 1;
@@ -741,8 +773,8 @@ static int step_all_lanes(Cache *c, bool with_logits, int mode, int next_prompt_
     for (size_t i = 0; i < c->lanes.size(); i++) {
         Lane &ln = c->lanes[i];
         cudaStream_t st = i == 0 ? m->stream : m->stream2;
-        const bool fused_adv = with_logits && mode == 1;
-        WB_CHECK(decode_step(c, ln, st, with_logits, false, fused_adv));
+        const bool fused_adv = with_logits && mode >= 1;
+        WB_CHECK(decode_step(c, ln, st, with_logits, false, fused_adv, mode == 2 ? PREFILL_LEN : 1));
         if (!fused_adv) WB_CHECK(greedy_advance(st, ln.g, ln.B, mode, next_prompt_token, ln.next));
     }
     if (two) {
@@ -757,19 +789,24 @@ static int greedy_loop(Cache *c) {
     cudaStream_t st = m->stream;
     const int n_lanes = (int)c->lanes.size();
     // prefill: the reference runs the 4 prompt ids as one q_len = 4 forward with a causal mask
-    // (whisper.mojo:195-197); feeding them one by one through the cached step computes the same
-    // thing (masked scores are exp(-1e10 - max) = 0 there) and only the last position's logits are used.
-    for (int i = 0; i < 4; i++) {
-        if (i < 3) WB_CHECK(step_all_lanes(c, false, 0, m->cfg.prompt[i + 1]));
-        else WB_CHECK(step_all_lanes(c, true, 1, 0));
+    // (whisper.mojo:195-197) -- decode_step with q_len = 4.  prefill_impl = 0 feeds them one by one through the
+    // cached step instead, which computes the same thing (masked scores are exp(-1e10 - max) = 0 there; only the
+    // last position's logits are used) with 3 more forwards; the two forms produce the same ids (tested).
+    if (m->prefill_impl) {
+        WB_CHECK(step_all_lanes(c, true, 2, 0));
+    } else {
+        for (int i = 0; i < 4; i++) {
+            if (i < 3) WB_CHECK(step_all_lanes(c, false, 0, m->cfg.prompt[i + 1]));
+            else WB_CHECK(step_all_lanes(c, true, 1, 0));
+        }
     }
     const bool graph = m->use_graph && !m->profile_attn;
-    if (c->graph_exec && c->graph_key != (m->decode_fused | (m->skip_done << 1) | ((int)g_pdl << 2))) {
+    if (c->graph_exec && c->graph_key != (m->decode_fused | (m->skip_done << 2) | ((int)g_pdl << 3))) {
         cudaGraphExecDestroy(c->graph_exec);  // captured under other launch options: capture again
         c->graph_exec = nullptr;
     }
     if (graph && !c->graph_exec) {
-        c->graph_key = m->decode_fused | (m->skip_done << 1) | ((int)g_pdl << 2);
+        c->graph_key = m->decode_fused | (m->skip_done << 2) | ((int)g_pdl << 3);
         cudaGraph_t gr = nullptr;
         WB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int64_t l0 = g_launches.load();

@@ -66,11 +66,14 @@ struct Model {
     int gemm_impl = 1, attn_impl = 1, frontend_impl = 1,  // frontend: 0 = fp32 FMA DFT, 1 = TF32x3 tensor-core DFT
          use_graph = 1, profile_attn = 0, enc_batch = 128, wave_max = 2048, small_batch = 0,
         decode_split_k = 1,  // split-K residual GEMMs + fused residual/LayerNorm in the decode step
-        decode_fused = 1,  // 1 = the dense work between two attention kernels runs as one persistent chain kernel
-                           // (decode_chain.cu: 4 L + 3 kernels per step instead of 12 L + 4); 0 = round 1's kernel per op
+        decode_fused = 2,  // 1 = the dense work between two attention kernels runs as one persistent chain kernel
+                           // (decode_chain.cu: 4 L + 3 kernels per step instead of 12 L + 4); 0 = round 1's kernel per op;
+                           // 2 = chain kernels for waves of <= FUSED_MAX_WAVE chunks (latency bound), kernel per op above
         decode_lanes = 1,  // 2 = two half-batches on two streams (measured: no gain, the HBM-bound kernel fills every SM)
         cross_impl = 1,    // 0 = per-layer cross K/V cache (reference form), 1 = absorbed form over enc_out (D <= 384)
-        skip_done = 1;     // 1 = chunks that produced EOT drop out of the attention kernels (live list rebuilt every 16 steps)
+        skip_done = 1,     // 1 = chunks that produced EOT drop out of the attention kernels (live list rebuilt every 16 steps)
+        prefill_impl = 1;  // 1 = the 4 prompt ids run as ONE q_len = 4 forward with the causal block path (whisper.mojo:195-197);
+                           // 0 = fed one by one through the cached step (same ids, 3 more forwards)
     int *stop_sched = nullptr;  // device [stop_sched_n]: forced lengths per chunk of a transcribe call (wm_set_stop_lengths)
     int stop_sched_n = 0;
     Layout lay;
@@ -99,6 +102,10 @@ struct Model {
     size_t stage_in_cap = 0, stage_out_cap = 0;
 };
 
+// The reference's prompt: 4 ids run as one q_len = 4 forward (whisper.mojo:190-197).
+static constexpr int PREFILL_LEN = 4;
+static constexpr int FUSED_MAX_WAVE = 1280;  // decode_fused = 2: largest wave the chain kernels serve (measured crossover)
+
 // A lane = a contiguous sub-batch of the cache's chunks with its own decode workspace and step state.
 // Two lanes run on two streams inside one CUDA graph: one lane's small latency-bound kernels overlap the
 // other lane's HBM-bound cross-attention.
@@ -106,6 +113,7 @@ struct Lane {
     int B = 0, b_off = 0;
     float *x = nullptr, *part_val = nullptr, *attn_ws = nullptr, *logits = nullptr, *part = nullptr;
     h16 *xn = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *qp = nullptr, *ctx = nullptr;
+    h16 *pf_k = nullptr, *pf_v = nullptr;  // prefill: k / v rows [PREFILL_LEN * B][D] on their way into the cache
     int *part_idx = nullptr, *next = nullptr;
     int cross_splits = 1;
     int part_splits = 4;  // slices the split-K partial buffer `part` holds
@@ -148,7 +156,7 @@ int cache_create(Model *m, int B, int max_len, bool want_logits, int n_lanes, Ca
 void cache_destroy(Cache *c);
 int cache_reset(Cache *c);
 int cache_set_encoder(Cache *c, const float *enc_out_dev);
-int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits, bool advance);
+int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool store_logits, bool advance, int q_len = 1);
 int model_transcribe(Model *m, const float *mel_dev, const float *pcm_dev, int n, int32_t *out_tokens_dev,
                      int32_t *out_len_dev, const float *in_host = nullptr);
 int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_t *forced_host, int n_forced,

@@ -472,11 +472,15 @@ def run_b200(args):
         # decode lane and no graph so the launches neither overlap other kernels nor hide inside a graph
         model.set_option("profile_attn", 1)
         model.set_option("decode_lanes", 1)
+        # every timed launch is the decode-step kernel (one query row per chunk): the prompt goes through four cached
+        # steps in this pass (same ids; the one-forward prefill attends for two prompt rows per pass)
+        model.set_option("prefill_impl", 0)
         model.transcribe_pcm_batch(pcm)
         torch.cuda.synchronize()
         tot_ms, n_launch = model.last_cross_attention_timing()
         prof_decode_ms = model.last_timing()["decode_ms"]
         model.set_option("profile_attn", 0)
+        model.set_option("prefill_impl", 1)
         model.set_option("decode_lanes", args.lanes)
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # algorithmic bytes per launch of the absorbed cross-attention: every chunk's 16-bit enc_out read once
@@ -546,11 +550,11 @@ def run_b200(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         # decode: bytes one greedy step must move (16-bit): weights touched once + per chunk the encoder output once
         # per layer (absorbed cross-attention) + the self K/V rows written so far; averaged over the decoder forwards.
-        # n_fwd = 4 prompt positions + max_iters: the reference's q_len = 4 prefill (whisper.mojo:195-197) runs here as
-        # 4 single-token steps, so 199 forwards, not SURVEY 8d's 196.
-        n_fwd = 4 + cfg.max_iters
+        # n_fwd = 1 + max_iters = 196: the reference's q_len = 4 prefill (whisper.mojo:195-197) runs as ONE
+        # forward (prefill_impl = 1), then max_iters cached steps; step k attends over 5 + k self K/V rows.
+        n_fwd = 1 + cfg.max_iters
         w_step = L * (4 * D * D + 2 * H * D * D + 2 * D * F) + V * D  # self qkv/o, folded cross q'/o', mlp, logits
-        t_avg = (n_fwd - 1) / 2.0
+        t_avg = (cfg.max_iters * (5 + (cfg.max_iters - 1) / 2.0) + 10) / n_fwd
         step_bytes = 2 * w_step + C * 2 * (L * S * D + 2 * L * t_avg * D)
         dec_gbs = step_bytes * n_fwd / (phases["decode_ms"] * 1e-3) / 1e9
         fe_bytes = C * (cfg.n_samples * 4 + cfg.n_mels * cfg.n_frames * 4)
@@ -559,7 +563,7 @@ def run_b200(args):
                         "flop_per_chunk": enc_flop, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 runs at the same kind::f16 rate)"},
             "decode_step": {"bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s",
                             "frac": dec_gbs / hbm_peak, "bytes_per_step": step_bytes, "forwards": n_fwd,
-                            "note": "199 forwards = 4 single-token prompt steps + 195 greedy steps (SURVEY 8d counts the prompt as one q_len = 4 forward: 196)"},
+                            "note": "196 forwards = one q_len = 4 prompt forward + 195 greedy steps (SURVEY 8d); algorithmic bytes: 16-bit weights once, enc_out once per layer, the self K/V rows written so far"},
             "frontend": {"bound": "hbm", "achieved": fe_bytes / (phases["frontend_ms"] * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": fe_bytes / (phases["frontend_ms"] * 1e-3) / 1e9 / hbm_peak,
                          "note": "pcm f32 in + log-mel f32 out; the TF32x3 DFT adds 2.9 GFLOP-equivalent per chunk",
@@ -609,7 +613,7 @@ def run_b200(args):
                                     "(BASELINE.json configs[4]): " if small else
                                     "whisper-tiny batched greedy transcription (BASELINE.json configs[3]): ") +
                                    f"{n_total} synthetic 30 s chunks per step sharded over {world} GPU(s), pcm -> log-mel -> encoder -> "
-                                   "199 decoder forwards (EOT never fires with random weights)",
+                                   "196 decoder forwards: the 4-id prompt as one q_len = 4 forward + 195 greedy steps (EOT never fires with random weights)",
                        "chunks_per_gpu": C, "global_chunks": n_total, "weights": "random-init whisper-%s shapes" % ("small" if small else "tiny"),
                        "precision": f"{prec} weights / GEMM operands / KV cache, fp32 accumulation, fp32 residual stream, LayerNorm, softmax and logits",
                        "l2": "inputs (pcm %.1f GB per GPU) larger than the 126 MB L2; no explicit flush" % (pcm.numel() * 4 / 1e9),

@@ -40,6 +40,7 @@ struct ChainPhase {
     int tma_out;        // plain [rows][N] output: coalesced bulk tensor stores instead of per-thread row stores
     const void *w_base;  // the phase's weight matrix, for the L2 prefetch at kernel start
     unsigned long long w_bytes;
+    unsigned long long w_per_cta;  // bytes of it each CTA prefetches (multiple of 4 KB; set at launch-geometry time)
     GemmDev d;          // rows_per_batch = M, batches = split_k ("batch" b = K slice), num_kb per slice
     int type, tiles_n, splits;
     // row phase
@@ -64,6 +65,7 @@ struct ChainParams {
 struct ChainPlan {
     ChainParams P;
     int grid = 1;
+    int grid_final = 0;  // CTAs of the launch once the device is known (chain_grid)
 };
 
 #define CH_STAMP(p, role, ev)                                                                          \
@@ -138,7 +140,9 @@ __device__ __forceinline__ void chain_rows(const ChainPhase &ph, int row0, int M
     } else {
         const long long split_stride = (long long)M * D;
         // every load of both rows is issued before the first use: one L2 round trip, not one per slice
-        constexpr int SB = NV <= 3 ? 4 : 2;  // slices whose loads are in flight together (one L2 round trip per SB slices)
+        // slices whose loads are in flight together (one L2 round trip per SB slices).  Six at once (the longest
+        // reduction of d_model <= 384 in one round trip) spills at the kernel's 168-register cap and measured slower.
+        constexpr int SB = NV <= 3 ? 4 : 2;
         float4 pp[SB][R][NV];
 #pragma unroll
         for (int r = 0; r < R; r++)
@@ -234,6 +238,10 @@ __device__ __forceinline__ void chain_epilogue(const GemmDev &p, int b, int m, i
 }
 
 // NV = d_model / 128 (the row phases keep a row in registers).
+// The parameter block stays a __grid_constant__ kernel parameter: a copy in global memory that all threads pull into
+// shared memory at kernel start was tried (to avoid first-touch constant-cache misses per phase and role) and measured
+// slower -- 68.5 -> 72.2 ms at batch 1, 114.5 -> 117.6 at 256 chunks: the extra global round trip in front of the CTA
+// barrier and tensor maps fetched from global memory cost more than the misses.
 template <int NV>
 __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -248,34 +256,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
     uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + 2;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
     float *bias_smem = reinterpret_cast<float *>(tiles + RING_BYTES + CH_STAGE_OUT_BYTES + 256);  // [8][128]
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = (int)gridDim.x;
-    if (P.dbg && threadIdx.x == 0 && blockIdx.x < 256) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + blockIdx.x] = ptx::globaltimer_ns();
+    if (P.dbg && threadIdx.x == 0 && blockIdx.x < 248) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + blockIdx.x] = ptx::globaltimer_ns();
 
-    if (warp == 2) {
-        // The attention kernel that ran before this one streamed gigabytes through the L2, so every weight matrix of
-        // this chain is cold; its first reader would pay the HBM latency per ring refill (4 x 32 KB in flight per SM
-        // = ~75 GB/s per SM, measured).  Each CTA asks the L2 for its 1/G slice of every matrix of the chain right
-        // away, so the later phases' weights arrive while the first phases run.
-        for (int p = 0; p < P.n_phases; p++) {
-            const ChainPhase &ph = P.ph[p];
-            if (ph.type != PH_GEMM || !ph.w_bytes) continue;
-            const unsigned long long per = ((ph.w_bytes / G) + 4095ull) & ~4095ull;  // 4 KB pieces, one per lane and round
-            const unsigned long long lo = per * blockIdx.x, hi = lo + per < ph.w_bytes ? lo + per : ph.w_bytes;
-            for (unsigned long long off = lo + 4096ull * lane; off < hi; off += 4096ull * 32) {
-                const unsigned n = (unsigned)(hi - off < 4096ull ? hi - off : 4096ull) & ~15u;
-                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(ph.w_base) + off), "r"(n) : "memory");
-            }
-        }
+
+#define CH_PRO(k)                                                                                       \
+    do {                                                                                                \
+        if (P.dbg && blockIdx.x == 0 && lane == 0) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + 504 + (k)] = ptx::globaltimer_ns(); \
+    } while (0)
+    // Prologue, spread over the warps so that the CTA barrier falls ~0.5 us after the kernel starts (one thread walking
+    // every phase's tensor maps and one warp computing the L2 prefetch ranges in front of the barrier took 2.2-2.7 us
+    // per launch, nine launches per decode step: prologue timestamps in profiles/)
+    if (warp == 3 && lane < P.n_phases && P.ph[lane].type == PH_GEMM) {  // lane p: the tensor maps of phase p
+        ptx::prefetch_tmap(&P.ph[lane].a_map);
+        ptx::prefetch_tmap(&P.ph[lane].b_map);
+        if (P.ph[lane].tma_out) ptx::prefetch_tmap(&P.ph[lane].o_map);
     }
     if (warp == 0 && lane == 0) {
-        for (int p = 0; p < P.n_phases; p++)
-            if (P.ph[p].type == PH_GEMM) {
-                ptx::prefetch_tmap(&P.ph[p].a_map);
-                ptx::prefetch_tmap(&P.ph[p].b_map);
-                if (P.ph[p].tma_out) ptx::prefetch_tmap(&P.ph[p].o_map);
-            }
         for (int s = 0; s < STAGES; s++) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
@@ -285,15 +283,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
             ptx::mbar_init(&tmem_empty[s], 8);
         }
         ptx::fence_barrier_init();
+        CH_PRO(1);  // tensor maps prefetched, barriers initialised
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_holder, 256);
         ptx::tmem_relinquish();
+        CH_PRO(2);  // TMEM allocated
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (warp == 3) CH_PRO(3);  // past the CTA barrier
+    if (warp >= 2) {
+        // The attention kernel that ran before this one streamed gigabytes through the L2, so every weight matrix of
+        // this chain is cold; its first reader would pay the HBM latency per ring refill.  Each CTA asks the L2 for
+        // its 1/G slice of every matrix of the chain right away (4 KB pieces, one per epilogue thread: a handful of
+        // instructions each, issued while these warps would otherwise wait for the first accumulator), so the later
+        // phases' weights arrive while the first phases run.
+        const unsigned tid = (unsigned)(warp - 2) * 32u + (unsigned)lane;
+        for (int p = 0; p < P.n_phases; p++) {
+            const ChainPhase &ph = P.ph[p];
+            if (ph.type != PH_GEMM || !ph.w_bytes) continue;
+            const unsigned long long lo = ph.w_per_cta * blockIdx.x, hi = lo + ph.w_per_cta < ph.w_bytes ? lo + ph.w_per_cta : ph.w_bytes;
+            for (unsigned long long off = lo + 4096ull * tid; off < hi; off += 4096ull * 256) {
+                const unsigned n = (unsigned)(hi - off < 4096ull ? hi - off : 4096ull) & ~15u;
+                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(ph.w_base) + off), "r"(n) : "memory");
+            }
+        }
+        if (warp == 2) CH_PRO(0);  // L2 prefetches issued
+    }
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -356,6 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                     for (int kb = 0; kb < nkb; kb++) {
                         ptx::mbar_wait(&full_bar[stage], phase);
                         if (t == (int)blockIdx.x && kb == 0) CH_STAMP(p, 1, 0);
+                        if (t == (int)blockIdx.x && kb >= 1 && kb <= 6) CH_STAMP(p, 1, 1 + kb);  // k-blocks 1..6 have landed
                         ptx::tc_fence_after();
                         const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES), 1, 64);
                         const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES), 1, 64);
@@ -472,8 +492,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
                 for (int u = blockIdx.x; u < n_units; u += G) {
                     const int mt = (u * UNIT_ROWS) / BM;
                     if (p > 0) {
-                        if (lane == 0) chain_wait(P.counters + (p - 1) * P.tiles_m + mt, chain_target(P, p - 1, mt));
-                        __syncwarp();
+                        // ONE poller per CTA: eight warps spinning on the same counter line from every CTA kept its L2
+                        // slice saturated with polls, which is also where the producers' arrivals have to land
+                        if (ew == 0 && lane == 0) chain_wait(P.counters + (p - 1) * P.tiles_m + mt, chain_target(P, p - 1, mt));
+                        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
                     }
                     if (u == (int)blockIdx.x && ew == 0 && lane == 0) CH_STAMP(p, 2, 0);
                     const int row0 = u * UNIT_ROWS + ew * (UNIT_ROWS / 8);
@@ -491,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (P.dbg && threadIdx.x == 0 && blockIdx.x < 256) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + 256 + blockIdx.x] = ptx::globaltimer_ns();
+    if (P.dbg && threadIdx.x == 0 && blockIdx.x < 248) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + 256 + blockIdx.x] = ptx::globaltimer_ns();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
 }
 
@@ -513,6 +535,12 @@ int chain_split_k(int K) {
     return s;
 }
 
+static unsigned long long *g_chain_dbg = nullptr;
+void chain_debug_init() {  // development aid: the timestamp buffer must exist before any stream capture
+    if (getenv("WB_CHAIN_DBG") && !g_chain_dbg &&
+        cudaMalloc((void **)&g_chain_dbg, ((size_t)CHAIN_MAX_PHASES * 3 * 8 + 512) * 8) != cudaSuccess)
+        g_chain_dbg = nullptr;
+}
 ChainPlan *chain_plan_create(int M, int D, int *counters) {
     ChainPlan *p = new ChainPlan();
     p->P.n_phases = 0, p->P.M = M, p->P.D = D, p->P.tiles_m = cdiv(M, BM), p->P.counters = counters, p->P.dbg = nullptr;
@@ -584,7 +612,6 @@ int chain_plan_add_rows(ChainPlan *pl, const ChainRows &r) {
 }
 
 // WB_CHAIN_DBG=1: every launch records CTA 0's timestamps; chain_debug_dump prints those of the LAST launch
-static unsigned long long *g_chain_dbg = nullptr;
 static int g_chain_dbg_phases = 0;
 void chain_debug_dump() {
     if (!g_chain_dbg) return;
@@ -595,7 +622,7 @@ void chain_debug_dump() {
     unsigned long long t0 = ~0ull, s_max = 0, e_min = ~0ull, e_max = 0;
     const size_t np_ = (size_t)CHAIN_MAX_PHASES * 3 * 8;
     int n_cta = 0;
-    for (size_t i = 0; i < 256; i++)
+    for (size_t i = 0; i < 248; i++)
         if (h[np_ + i]) {
             n_cta++;
             t0 = std::min(t0, h[np_ + i]), s_max = std::max(s_max, h[np_ + i]);
@@ -604,12 +631,14 @@ void chain_debug_dump() {
     fprintf(stderr, "%d CTAs: started within %.2f us, ended between %.2f and %.2f us after the first start (CTA 0: %.2f .. %.2f)\n", n_cta,
             (double)(s_max - t0) / 1e3, (double)(e_min - t0) / 1e3, (double)(e_max - t0) / 1e3, (double)(h[np_] - t0) / 1e3,
             (double)(h[np_ + 256] - t0) / 1e3);
+    fprintf(stderr, "prologue of CTA 0 (us): L2 prefetches issued %.2f, tensor maps + barriers %.2f, TMEM allocated %.2f, past the CTA barrier %.2f\n",
+            (double)(h[np_ + 504] - t0) / 1e3, (double)(h[np_ + 505] - t0) / 1e3, (double)(h[np_ + 506] - t0) / 1e3, (double)(h[np_ + 507] - t0) / 1e3);
     fprintf(stderr, "chain timestamps of the last launch, CTA 0, first tile / unit of each phase (us since the first stamp)\n"
-                    "phase | producer: start B_issued dep_ready A_issued | mma: first_full commit | epi/rows: ready stored signalled\n");
+                    "phase | producer: start B_issued dep_ready A_issued | mma: first_full commit kb1..kb6 landed | epi/rows: ready stored signalled\n");
     for (int p = 0; p < g_chain_dbg_phases; p++) {
         fprintf(stderr, "%5d |", p);
         for (int r = 0; r < 3; r++) {
-            const int ne = r == 0 ? 4 : (r == 1 ? 2 : 3);
+            const int ne = r == 0 ? 4 : (r == 1 ? 8 : 3);  // mma: first_full, commit, then the arrival of k-blocks 1..6
             for (int e = 0; e < ne; e++) {
                 const unsigned long long v = h[((size_t)p * 3 + r) * 8 + e];
                 if (v) fprintf(stderr, " %8.2f", (double)(v - t0) / 1e3);
@@ -621,22 +650,30 @@ void chain_debug_dump() {
     }
 }
 
-int chain_launch(cudaStream_t st, const ChainPlan *pl) {
+// Fix the launch geometry (CTAs of the plan on this device, each phase's per-CTA L2 prefetch slice), once all phases
+// are added.
+int chain_plan_finalize(ChainPlan *pl) {
     WB_ARG(pl && pl->P.n_phases > 0, "chain: empty plan");
-    static const bool dbg_on = getenv("WB_CHAIN_DBG") != nullptr;
-    ChainParams Pd;
-    const ChainParams *Pp = &pl->P;
-    if (dbg_on) {
-        if (!g_chain_dbg && cudaMalloc((void **)&g_chain_dbg, ((size_t)CHAIN_MAX_PHASES * 3 * 8 + 512) * 8) != cudaSuccess) g_chain_dbg = nullptr;
-        if (g_chain_dbg) {
-            cudaMemsetAsync(g_chain_dbg, 0, ((size_t)CHAIN_MAX_PHASES * 3 * 8 + 512) * 8, st);
-            Pd = pl->P, Pd.dbg = g_chain_dbg, Pp = &Pd;
-            g_chain_dbg_phases = pl->P.n_phases;
-        }
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int G = std::min(pl->grid, sms);
+    for (int p = 0; p < pl->P.n_phases; p++) {
+        ChainPhase &ph = pl->P.ph[p];
+        if (ph.type == PH_GEMM) ph.w_per_cta = ((ph.w_bytes / (unsigned long long)G) + 4095ull) & ~4095ull;
+    }
+    pl->grid_final = G;
+    pl->P.dbg = g_chain_dbg;  // WB_CHAIN_DBG: every launch records CTA 0's timestamps
+    return WB_OK;
+}
+
+int chain_launch(cudaStream_t st, ChainPlan *pl) {
+    WB_ARG(pl && pl->grid_final > 0, "chain: plan was not finalized");
+    const int G = pl->grid_final;
+    if (pl->P.dbg) {
+        cudaMemsetAsync(pl->P.dbg, 0, ((size_t)CHAIN_MAX_PHASES * 3 * 8 + 512) * 8, st);
+        g_chain_dbg_phases = pl->P.n_phases;
+    }
     void (*kernel)(const ChainParams) = nullptr;
     switch (pl->P.D >> 7) {
         case 1: kernel = decode_chain_kernel<1>; break;
@@ -651,13 +688,13 @@ int chain_launch(cudaStream_t st, const ChainPlan *pl) {
     // Cooperative launch: the whole grid is resident at once (one CTA per SM), which the arrival counters need --
     // also when another stream's kernels compete for the SMs.
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(std::min(pl->grid, sms)), cfg.blockDim = dim3(TC_THREADS);
+    cfg.gridDim = dim3(G), cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = CH_SMEM_BYTES, cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    WB_CUDA(cudaLaunchKernelEx(&cfg, kernel, *Pp));
+    WB_CUDA(cudaLaunchKernelEx(&cfg, kernel, pl->P));
     WB_LAUNCHED();
     return WB_OK;
 }

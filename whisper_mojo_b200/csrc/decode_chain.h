@@ -62,10 +62,13 @@ int chain_plan_add_rows(ChainPlan *p, const ChainRows &r);
 int chain_plan_phases(const ChainPlan *p);
 // Number of ints of counter storage one plan needs (the caller zeroes them before every launch of the plan).
 size_t chain_counter_ints(int M);
-int chain_launch(cudaStream_t st, const ChainPlan *p);
+// Fixes the launch geometry (call once, after the last phase was added).
+int chain_plan_finalize(ChainPlan *p);
+int chain_launch(cudaStream_t st, ChainPlan *p);
 // Split-K factor for a residual GEMM with reduction length K (a property of the model, never of the batch size).
 int chain_split_k(int K);
 // Development aid: with WB_CHAIN_DBG set in the environment, prints CTA 0's per-phase timestamps of the last launch.
 void chain_debug_dump();
+void chain_debug_init();  // allocates the timestamp buffer (call outside stream capture, e.g. at model creation)
 
 }  // namespace wb

@@ -124,6 +124,7 @@ int model_create(const wm_config *cfg, void *stream, Model **out) {
         model_destroy(m);
         return WB_ERR_CUDA;
     }
+    chain_debug_init();
     int rc = frontend_tables_create(&m->ft, m->NM);
     if (rc != WB_OK) {
         model_destroy(m);
@@ -571,6 +572,24 @@ static int build_chain_plans(Cache *c, Lane &ln) {
             }
         }
     }
+    // launch geometry + upload of the parameter blocks (allocates: build_chain_plans runs outside stream capture)
+    for (ChainPlan *p : ln.plans) WB_CHECK(chain_plan_finalize(p));
+    WB_CHECK(chain_plan_finalize(ln.plan_last_nolog));
+    return WB_OK;
+}
+
+// Does a q_len = 1 step of this lane run the chain kernels?  (decode_fused = 2: by wave size, see decode_step)
+static bool lane_is_fused(const Cache *c, const Lane &ln) {
+    const Model *m = c->m;
+    static const bool fused_lanes = getenv("WB_FUSED_LANES") != nullptr;  // experiment: chain kernels on two lanes
+    const bool want_fused = m->decode_fused == 1 || (m->decode_fused == 2 && ln.B <= FUSED_MAX_WAVE);
+    return want_fused && m->gemm_impl == GEMM_IMPL_TC && (c->lanes.size() == 1 || fused_lanes) && m->D <= 768;
+}
+// Build the lanes' chain plans if the step will use them.  Allocates and copies, so every entry point calls it BEFORE
+// it queues / captures steps (greedy_loop, the step API, teacher forcing).
+static int prepare_chain_plans(Cache *c) {
+    for (Lane &ln : c->lanes)
+        if (lane_is_fused(c, ln) && ln.plans.empty()) WB_CHECK(build_chain_plans(c, ln));
     return WB_OK;
 }
 
@@ -616,9 +635,8 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
     // decode_fused = 2: by wave size.  The chain kernels win while the step is latency bound; from ~1.3 k chunks on the
     // phases are throughput bound and the CTA-pair GEMM kernels of the kernel-per-op form are ahead (B200, Tiny:
     // 1024 chunks 249.8 vs 252.8 ms, 1536: 349.8 vs 342.8, 2048: 445 vs 434; tools/fused_ab.py).  Same bits either way.
-    const bool want_fused = m->decode_fused == 1 || (m->decode_fused == 2 && B <= FUSED_MAX_WAVE);
-    const bool fused = q_len == 1 && want_fused && impl == GEMM_IMPL_TC && c->lanes.size() == 1 && D <= 768;
-    if (fused && ln.plans.empty()) WB_CHECK(build_chain_plans(c, ln));  // host-only work (tensor maps): capture safe
+    const bool fused = q_len == 1 && lane_is_fused(c, ln);
+    WB_ARG(!fused || !ln.plans.empty(), "decode_step: chain plans were not prepared");
     if (fused) {
         // 4 L + 3 kernels: chain | self-attn | chain | cross-attn | chain | ... | logits+argmax | argmax reduce
         WB_CUDA(cudaMemsetAsync(ln.counters, 0, ln.counter_bytes, st));  // arrival counters of this step's chains
@@ -643,7 +661,7 @@ int decode_step(Cache *c, Lane &ln, cudaStream_t st, bool with_logits, bool stor
                 a.splits = ln.cross_splits, a.ws = ln.attn_ws;
                 WB_CHECK(timed_kernel(m, st, TK_CROSS, [&] { return decode_attention(st, a); }));
             }
-            const ChainPlan *ca = (l + 1 == m->L && !with_logits) ? ln.plan_last_nolog : ln.plans[2 + 2 * l];
+            ChainPlan *ca = (l + 1 == m->L && !with_logits) ? ln.plan_last_nolog : ln.plans[2 + 2 * l];
             WB_CHECK(timed_kernel(m, st, TK_CHAIN_CA, [&] { return chain_launch(st, ca); }));
         }
     } else {
@@ -787,6 +805,7 @@ static int step_all_lanes(Cache *c, bool with_logits, int mode, int next_prompt_
 static int greedy_loop(Cache *c) {
     Model *m = c->m;
     cudaStream_t st = m->stream;
+    WB_CHECK(prepare_chain_plans(c));
     const int n_lanes = (int)c->lanes.size();
     // prefill: the reference runs the 4 prompt ids as one q_len = 4 forward with a causal mask
     // (whisper.mojo:195-197) -- decode_step with q_len = 4.  prefill_impl = 0 feeds them one by one through the
@@ -1040,6 +1059,7 @@ int cache_step_api(Cache *c, const int32_t *tokens_host, int start_pos, float *l
     Lane &ln = c->lanes[0];
     WB_ARG(!logits_host || ln.logits, "decode_step: cache was created without a logits buffer");
     WB_CHECK(set_step_state(c, c->host_len, start_pos, tokens_host));
+    WB_CHECK(prepare_chain_plans(c));
     WB_CHECK(decode_step(c, ln, m->stream, true, logits_host != nullptr, false));
     c->host_len++;
     if (logits_host)
@@ -1058,6 +1078,7 @@ int model_teacher_forced(Model *m, const float *enc_out_dev, int n, const int32_
     WB_CHECK(cache_create(m, n, std::min(m->T, (n_forced + 7) & ~7), true, 1, &c));
     Lane &ln = c->lanes[0];
     int rc = cache_set_encoder(c, enc_out_dev);
+    if (rc == WB_OK) rc = prepare_chain_plans(c);
     std::vector<int32_t> col(n);
     for (int i = 0; i < n_forced && rc == WB_OK; i++) {
         for (int b = 0; b < n; b++) col[b] = forced_host[(size_t)b * n_forced + i];

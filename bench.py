@@ -351,7 +351,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from whisper_mojo_b200 import WeightLoader, Whisper, WhisperConfig, _lib, synth
-    from whisper_mojo_b200.dist import gather_tokens, shard_range
+    from whisper_mojo_b200.dist import gather_tokens, shard_range, wait_for_rank0
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -579,7 +579,9 @@ def run_b200(args):
         except Exception as ex:
             parity = {"error": str(ex)[:300]}
     if world > 1:
-        dist.barrier()  # the other ranks wait for rank 0's checks before tearing the group down
+        # the other ranks wait for rank 0's checks before tearing the group down -- asleep on the store's socket, not
+        # spinning in a NCCL barrier (7 polling ranks on 16 cores made the OpenMP oracle several times slower)
+        wait_for_rank0("parity")
 
     cpu = cpu_hf = bf16_line = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -111,6 +111,37 @@ def test_gather_tokens_world2_gloo(n_total):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _wait_worker(rank, world, port, q):
+    import time
+
+    from whisper_mojo_b200.dist import wait_for_rank0
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t0 = time.time()
+    if rank == 0:
+        time.sleep(1.5)  # rank 0's host-side work
+    wait_for_rank0("t")
+    q.put((rank, time.time() - t0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_wait_for_rank0_releases_the_other_ranks_only_after_rank0_world2_gloo():
+    """bench.py's end-of-run wait: ranks != 0 sleep on the rendezvous store until rank 0 is through its checks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wait_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[1] >= 1.0, res  # rank 1 was held until rank 0 arrived
+    assert res[0] < 60 and res[1] < 60
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the driver's reference arm): rank 0 prints ONE JSON line carrying the bench
     contract's keys with the CPU restatement's own value; other ranks exit 0 silently; the B200 arm refuses to run

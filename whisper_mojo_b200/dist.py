@@ -43,6 +43,29 @@ def gather_tokens(tokens, lens, n_total: int, group=None, dst: Optional[int] = 0
     return cat[:, :T].contiguous(), cat[:, T].contiguous()
 
 
+def wait_for_rank0(tag: str, timeout_s: float = 3600.0) -> None:
+    """Every rank calls this; ranks != 0 return once rank 0 has called it.  The wait SLEEPS on the rendezvous store's
+    socket (a c10d key wait) instead of spinning in a collective: a NCCL barrier keeps one host thread per waiting rank
+    polling at 100 %, which starves host-side work rank 0 still has to do (bench.py's CPU-oracle parity check ran
+    several times slower at 8 ranks on 16 cores for that reason).  Falls back to `dist.barrier()` if the process
+    group exposes no store."""
+    import datetime
+
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    try:
+        store = dist.distributed_c10d._get_default_store()
+        key = f"wb_rank0_done/{tag}"
+        if dist.get_rank() == 0:
+            store.set(key, "1")
+        else:
+            store.wait([key], datetime.timedelta(seconds=timeout_s))
+    except (AttributeError, RuntimeError):
+        dist.barrier()
+
+
 def transcribe_sharded(model, mel_or_pcm: np.ndarray, rank: int, world: int, pcm: bool = False):
     """Run this rank's shard of a host-resident batch; returns (tokens, lens, (lo, hi))."""
     lo, hi = shard_range(mel_or_pcm.shape[0], rank, world)

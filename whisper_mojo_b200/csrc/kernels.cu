@@ -18,7 +18,9 @@ namespace wb {
 enum { LN_PLAIN = 0, LN_EMBED = 1, LN_RESID = 2 };
 // MODE LN_RESID: x[row] += bias + sum_s part[s][row] (fixed order: deterministic) before the LayerNorm -- the second
 // half of a split-K residual GEMM fused with the LayerNorm that follows it; gamma == nullptr skips the LN output.
-template <int EMBED>
+// NVT: d_model / 128 at compile time (0 = read it from D): the LN_RESID form keeps a whole row and four slices of it in
+// registers, and sized for the general case (8 vectors) that is 224 registers = one CTA per SM.
+template <int EMBED, int NVT = 0>
 __global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x_in, const float *__restrict__ gamma,
                                                       const float *__restrict__ beta, int rows, int D,
                                                       h16 *__restrict__ out_h16,
@@ -41,26 +43,50 @@ __global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x
     if (row >= rows) return;
     // D is a multiple of 128 for every supported config (heads * 64 with an even head count);
     // up to 8 float4 per lane (D <= 1024) are kept in registers.
-    float4 v[8];
-    const int nvec = D >> 7;
+    constexpr int NVM = NVT ? NVT : 8;
+    float4 v[NVM];
+    const int nvec = NVT ? NVT : D >> 7;
     float s = 0.f, q = 0.f;
     if (EMBED == LN_RESID) {
+        // Every load of the row is issued before the first add: the row of x, the bias and the slices four at a time
+        // (two L2 round trips for six slices).  Vector by vector -- x, bias, slices, store, next vector -- this was
+        // ~6 serial round trips per row for d_model = 384.  The order of the adds is unchanged: x + bias + part[0] + ...
         float4 *xr = reinterpret_cast<float4 *>(x_out + (size_t)row * D);
+        float4 bb[NVM];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < NVM; i++)
             if (i < nvec) {
-                float4 a = xr[i * 32 + lane];
-                if (bias) {
-                    const float4 b = reinterpret_cast<const float4 *>(bias)[i * 32 + lane];
-                    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
-                }
-                for (int sidx = 0; sidx < n_split; sidx++) {
-                    const float4 pp = reinterpret_cast<const float4 *>(part + (size_t)sidx * split_stride + (size_t)row * D)[i * 32 + lane];
-                    a.x += pp.x, a.y += pp.y, a.z += pp.z, a.w += pp.w;
-                }
-                v[i] = a;
-                xr[i * 32 + lane] = a;
+                v[i] = xr[i * 32 + lane];
+                if (bias) bb[i] = reinterpret_cast<const float4 *>(bias)[i * 32 + lane];
             }
+        for (int s0 = 0; s0 < n_split; s0 += 4) {
+            float4 pp[4][NVM];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int i = 0; i < NVM; i++)
+                    if (i < nvec && s0 + k < n_split)
+                        pp[k][i] = reinterpret_cast<const float4 *>(part + (size_t)(s0 + k) * split_stride + (size_t)row * D)[i * 32 + lane];
+            if (s0 == 0 && bias) {
+#pragma unroll
+                for (int i = 0; i < NVM; i++)
+                    if (i < nvec) v[i].x += bb[i].x, v[i].y += bb[i].y, v[i].z += bb[i].z, v[i].w += bb[i].w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int i = 0; i < NVM; i++)
+                    if (i < nvec && s0 + k < n_split)
+                        v[i].x += pp[k][i].x, v[i].y += pp[k][i].y, v[i].z += pp[k][i].z, v[i].w += pp[k][i].w;
+        }
+        if (n_split == 0 && bias) {
+#pragma unroll
+            for (int i = 0; i < NVM; i++)
+                if (i < nvec) v[i].x += bb[i].x, v[i].y += bb[i].y, v[i].z += bb[i].z, v[i].w += bb[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < NVM; i++)
+            if (i < nvec) xr[i * 32 + lane] = v[i];
         if (!gamma) return;
     } else if (EMBED == LN_EMBED) {
         int tok, pos;
@@ -77,7 +103,7 @@ __global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x
         const float4 *te = reinterpret_cast<const float4 *>(tok_emb + (size_t)tok * D);
         const float4 *pe = reinterpret_cast<const float4 *>(pos_emb + (size_t)pos * D);
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < NVM; i++)
             if (i < nvec) {
                 float4 a = te[i * 32 + lane], b = pe[i * 32 + lane];
                 v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
@@ -86,11 +112,11 @@ __global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x
     } else {
         const float4 *xr = reinterpret_cast<const float4 *>(x_in + (size_t)row * D);
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < NVM; i++)
             if (i < nvec) v[i] = xr[i * 32 + lane];
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < NVM; i++)
         if (i < nvec) {
             s += v[i].x + v[i].y + v[i].z + v[i].w;
             q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
@@ -101,7 +127,7 @@ __global__ void __launch_bounds__(256) ln_h16_kernel(const float *__restrict__ x
     const float var = q / (float)D - mean * mean;
     const float inv_std = 1.0f / sqrtf(var + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < NVM; i++)
         if (i < nvec) {
             float4 g = reinterpret_cast<const float4 *>(gamma)[i * 32 + lane];
             float4 b = reinterpret_cast<const float4 *>(beta)[i * 32 + lane];
@@ -133,8 +159,20 @@ int resid_ln(cudaStream_t st, float *x, const float *part, int n_split, const fl
     WB_ARG(D % 128 == 0 && D <= 1024, "resid_ln: D=%d must be a multiple of 128 and <= 1024", D);
     WB_ARG(x && part && n_split >= 1 && (!gamma || (beta && out_h16)), "resid_ln: bad arguments");
     if (rows <= 0) return WB_OK;
-    WB_CUDA(launch_pdl(ln_h16_kernel<LN_RESID>, dim3(cdiv(rows, 8)), dim3(256), 0, st, nullptr, gamma, beta, rows, D, out_h16,
-                       nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, x, 1, make_int4(0, 0, 0, 0), nullptr, part, n_split, (long long)rows * D, bias));
+    auto go = [&](auto kernel) {
+        return launch_pdl(kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, (const float *)nullptr, gamma, beta, rows, D, out_h16,
+                          (float *)nullptr, (const float *)nullptr, (const float *)nullptr, (const int *)nullptr, (const int *)nullptr, 0, 0,
+                          x, 1, make_int4(0, 0, 0, 0), (int *)nullptr, part, n_split, (long long)rows * D, bias);
+    };
+    switch (D >> 7) {  // row + slices in registers: sized to d_model at compile time
+        case 1: WB_CUDA(go(ln_h16_kernel<LN_RESID, 1>)); break;
+        case 2: WB_CUDA(go(ln_h16_kernel<LN_RESID, 2>)); break;
+        case 3: WB_CUDA(go(ln_h16_kernel<LN_RESID, 3>)); break;
+        case 4: WB_CUDA(go(ln_h16_kernel<LN_RESID, 4>)); break;
+        case 5: WB_CUDA(go(ln_h16_kernel<LN_RESID, 5>)); break;
+        case 6: WB_CUDA(go(ln_h16_kernel<LN_RESID, 6>)); break;
+        default: WB_CUDA(go(ln_h16_kernel<LN_RESID, 0>)); break;
+    }
     WB_LAUNCHED();
     return WB_OK;
 }

@@ -241,6 +241,22 @@ struct DecodeAttnDev {
     const int *done;
 };
 
+// K / V rows travel global -> shared memory as 16-byte cp.async copies (L2 only), DA_STAGES iterations of 16 rows
+// ahead of their use: loads in flight cost no registers, so a warp keeps 3 x 4 x 16 B per lane outstanding instead of
+// 4 x 16 B (the kernel was bound by bytes in flight, not by HBM: ~73 KB per SM against the ~85 KB that 43 GB/s per SM
+// at ~2 us loaded latency need).  Every lane reads back only the slots it filled itself, so no barrier is involved,
+// and the arithmetic (lane -> row / dims mapping, order of the sums) is unchanged: same bits as the register version.
+static constexpr int DA_STAGES = 3;
+static constexpr int DA_STAGE_BYTES_PER_WARP = DA_STAGES * 4 * 32 * 16;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ uint4 ld_stream(const void *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -269,6 +285,20 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
     const int j1 = min(len, j0 + chunk);
     const int n = max(j1 - j0, 0);
     float *sc = s_scores + (size_t)h * p.smem_len;
+    // this warp's staging slots [stage][u][lane] of 16 bytes, behind the H score rows (16-byte aligned: smem_len % 4 == 0)
+    uint4 *stg = reinterpret_cast<uint4 *>(s_scores + (size_t)p.H * p.smem_len) + (size_t)h * (DA_STAGES * 4 * 32) + lane;
+    const int n_it = (n + 15) >> 4;
+    // queue the copies of iteration `it` (rows it*16 + sub + 4u, u < 4) of the matrix at `base`, one commit group each
+    auto issue = [&](const h16 *base, int it) {
+        if (it < n_it) {
+            const int i = it * 16 + sub;
+            uint4 *dst = stg + (it % DA_STAGES) * (4 * 32);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i + 4 * u < n) cp_async16(dst + u * 32, base + (size_t)(j0 + i + 4 * u) * p.D);
+        }
+        cp_async_commit();
+    };
 
     float qf[8];
     h8_to_float(*reinterpret_cast<const uint4 *>(p.q + (size_t)b * p.D + h * 64 + c * 8), qf);
@@ -278,13 +308,18 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
 
     // phase 1: scores
     float m = -1e10f;  // layers.mojo:188
-    for (int i0 = 0; i0 < n; i0 += 16) {  // warp-uniform trip count: the shuffles below need all 32 lanes
+#pragma unroll
+    for (int s = 0; s < DA_STAGES - 1; s++) issue(Kb, s);
+    for (int i0 = 0, it = 0; i0 < n; i0 += 16, it++) {  // warp-uniform trip count: the shuffles below need all 32 lanes
         const int i = i0 + sub;
+        issue(Kb, it + DA_STAGES - 1);  // refills the slot read in the previous iteration
+        cp_async_wait<DA_STAGES - 1>();
         uint4 kv[4];
+        const uint4 *src = stg + (it % DA_STAGES) * (4 * 32);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             int jj = i + 4 * u;
-            kv[u] = (jj < n) ? ld_stream(Kb + (size_t)(j0 + jj) * p.D) : make_uint4(0, 0, 0, 0);
+            kv[u] = (jj < n) ? src[u * 32] : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -306,6 +341,9 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
     }
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    cp_async_wait<0>();  // (only empty groups are left) every slot is free again:
+#pragma unroll
+    for (int s = 0; s < DA_STAGES - 1; s++) issue(Vb, s);  // the first V rows travel under the softmax
     __syncwarp();
     // phase 2: exp and sum
     float l = 0.f;
@@ -318,13 +356,16 @@ __global__ void __launch_bounds__(384) decode_attn_kernel(const DecodeAttnDev p)
     __syncwarp();
     // phase 3: weighted sum of V
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i0 = 0; i0 < n; i0 += 16) {
+    for (int i0 = 0, it = 0; i0 < n; i0 += 16, it++) {
         const int i = i0 + sub;
+        issue(Vb, it + DA_STAGES - 1);
+        cp_async_wait<DA_STAGES - 1>();
         uint4 vv[4];
+        const uint4 *src = stg + (it % DA_STAGES) * (4 * 32);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             int jj = i + 4 * u;
-            vv[u] = (jj < n) ? ld_stream(Vb + (size_t)(j0 + jj) * p.D) : make_uint4(0, 0, 0, 0);
+            vv[u] = (jj < n) ? src[u * 32] : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -397,7 +438,7 @@ int decode_attention_splits(int B, int len, int H) {
     for (int s = 1; s <= max_splits; s++) {
         int chunk = ((len + s - 1) / s + 3) & ~3;
         // resident CTAs per SM for this shared-memory footprint, from the occupancy calculator
-        size_t smem = (size_t)H * (chunk + 4) * sizeof(float);
+        size_t smem = (size_t)H * (chunk + 4) * sizeof(float) + (size_t)H * DA_STAGE_BYTES_PER_WARP;
         ensure_dyn_smem(decode_attn_kernel, smem);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel, H * 32, smem) != cudaSuccess)
@@ -427,7 +468,7 @@ int decode_attention(cudaStream_t st, const DecodeAttnArgs &a) {
     WB_ARG(a.len_dev || a.len_const > 0 || p.q_len > 1, "decode_attention: no key length");
     int chunk = (a.max_len + a.splits - 1) / a.splits;
     p.smem_len = ((chunk + 3) & ~3) + 4;
-    size_t smem = (size_t)a.H * p.smem_len * sizeof(float);
+    size_t smem = (size_t)a.H * p.smem_len * sizeof(float) + (size_t)a.H * DA_STAGE_BYTES_PER_WARP;
     WB_CUDA(ensure_dyn_smem(decode_attn_kernel, smem));
     dim3 grid(a.B, a.splits);
     WB_CUDA(launch_pdl(decode_attn_kernel, grid, dim3(a.H * 32), smem, st, p));

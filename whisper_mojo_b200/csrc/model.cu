@@ -929,6 +929,11 @@ static int model_transcribe_impl(Model *m, const float *mel_dev, const float *pc
         cudaMemGetInfo(&free_b, &total_b);
         size_t per_chunk = ((size_t)m->L * 2 * T_cache + (m->cross_impl == 1 ? (size_t)m->S : (size_t)m->L * 2 * m->S)) *
                            m->D * sizeof(h16);
+        // + the decode workspace: PREFILL_LEN rows per chunk of x (fp32), xn / q / k / v / attn, h, the split-K partials
+        // (at most K / 384 slices of fp32 [D]) and, in the absorbed form, q' and ctx [H * D]
+        const size_t HD = (size_t)m->H * m->D;
+        per_chunk += (size_t)PREFILL_LEN * ((size_t)m->D * (4 + 5 * sizeof(h16)) + (size_t)m->F * sizeof(h16) +
+                                            (std::max<size_t>(4, HD / 384 + 1)) * m->D * 4 + 2 * HD * sizeof(h16));
         size_t cap = std::max<size_t>(1, (free_b / 2) / per_chunk);
         wave = (int)std::min<size_t>(wave, cap);
     }

@@ -581,7 +581,7 @@ def run_b200(args):
     if world > 1:
         # the other ranks wait for rank 0's checks before tearing the group down -- asleep on the store's socket, not
         # spinning in a NCCL barrier (7 polling ranks on 16 cores made the OpenMP oracle several times slower)
-        wait_for_rank0("parity")
+        wait_for_rank0("parity", timeout_s=900.0)
 
     cpu = cpu_hf = bf16_line = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

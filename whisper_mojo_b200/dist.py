@@ -62,8 +62,10 @@ def wait_for_rank0(tag: str, timeout_s: float = 3600.0) -> None:
             store.set(key, "1")
         else:
             store.wait([key], datetime.timedelta(seconds=timeout_s))
-    except (AttributeError, RuntimeError):
+    except AttributeError:  # no store on this process group: the collective form
         dist.barrier()
+    except RuntimeError:  # rank 0 never arrived within timeout_s: give up waiting, the caller tears the group down
+        pass
 
 
 def transcribe_sharded(model, mel_or_pcm: np.ndarray, rank: int, world: int, pcm: bool = False):

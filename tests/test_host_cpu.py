@@ -121,7 +121,7 @@ def _wait_worker(rank, world, port, q):
     t0 = time.time()
     if rank == 0:
         time.sleep(1.5)  # rank 0's host-side work
-    wait_for_rank0("t")
+    wait_for_rank0("t", timeout_s=60.0)
     q.put((rank, time.time() - t0))
     dist.barrier()
     dist.destroy_process_group()

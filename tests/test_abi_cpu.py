@@ -100,3 +100,14 @@ def test_cpp_driver_links_against_the_abi_and_fails_loudly_without_a_gpu(tmp_pat
         pytest.skip("a GPU is present: the run is covered by the gpu test")
     r = subprocess.run([exe, str(tmp_path / "missing.bin")], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "no CUDA device" in r.stderr and "Token IDs" not in r.stdout
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """wm_set_option is a string-keyed entry point: every key the library accepts (csrc/api.cu) must be described in
+    include/whisper_b200.h, the only document an FFI caller reads."""
+    api = open(os.path.join(ROOT, "whisper_mojo_b200", "csrc", "api.cu")).read()
+    keys = sorted(set(re.findall(r'!strcmp\(key, "([a-z_0-9]+)"\)', api)))
+    assert len(keys) >= 10, keys
+    header = open(HEADER).read()
+    missing = [k for k in keys if f'"{k}"' not in header]
+    assert not missing, f"options without a description in the header: {missing}"

@@ -189,6 +189,22 @@ class OracleWhisper:
                                 max_iters, _ip(prompt), cfg.eot)
         return toks[:n].copy()
 
+    def decoder_forward_sequence(self, enc_out: np.ndarray, calls) -> np.ndarray:
+        """WhisperDecoder.forward (whisper.mojo:130-167) called once per entry of `calls` = [(tokens, start_pos), ...]
+        on one fresh KVCache; returns the logits of the LAST call's last position.  q_len > 1 takes the reference's
+        block path with the causal fill (layers.mojo:273-342), q_len == 1 the cached decode path (:186-272)."""
+        cfg = self.cfg
+        enc = np.ascontiguousarray(enc_out, np.float32)
+        cache = lib().wo_kvcache_create(self._m, cfg.n_text_ctx)
+        logits = np.empty(cfg.vocab_size, np.float32)
+        try:
+            for toks, start_pos in calls:
+                t = np.ascontiguousarray(toks, np.int32)
+                lib().wo_decoder_forward(self._m, cache, _ip(t), t.size, _fp(enc), 1, int(start_pos), _fp(logits), None)
+        finally:
+            lib().wo_kvcache_destroy(cache)
+        return logits
+
     def teacher_forced(self, enc_out: np.ndarray, forced: np.ndarray, pos_quirk=None) -> np.ndarray:
         """forced[0:4] is the prefill; returns logits [len(forced)-3, vocab]."""
         cfg = self.cfg

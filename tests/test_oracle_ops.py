@@ -57,3 +57,27 @@ def test_argmax_first_max_wins():
     x[[17, 40]] = 3.0
     assert O.argmax(x) == 17
     assert O.argmax(np.full(5, -1.0, np.float32)) == 0
+
+
+def test_block_prefill_with_causal_fill_equals_cached_single_token_steps():
+    """whisper.mojo:195-197 runs the 4 prompt ids as ONE decoder.forward through the block path, where keys j > i are
+    filled with -1e10 before the softmax (layers.mojo:304-320): in fp32 exp(-1e10 - max) is exactly 0, so the result
+    must equal feeding the ids one by one through the cached decode path (layers.mojo:186-272) up to summation order.
+    This is the property the GPU prefill rests on (one q_len = 4 forward == four cached steps, tests/test_gpu_model.py)."""
+    from whisper_mojo_b200 import WhisperConfig, synth
+
+    cfg = WhisperConfig.micro()
+    w = synth.make_weights(cfg, seed=3)
+    om = O.OracleWhisper(cfg, w)
+    enc = om.encode(synth.make_mel(1, cfg, 5)[0])
+    p = list(cfg.prompt)
+    block = om.decoder_forward_sequence(enc, [(p, 0)])
+    steps = om.decoder_forward_sequence(enc, [([p[0]], 0), ([p[1]], 1), ([p[2]], 2), ([p[3]], 3)])
+    mixed = om.decoder_forward_sequence(enc, [(p[:2], 0), (p[2:], 2)])  # a block call on a non-empty cache (past_len = 2)
+    scale = float(np.abs(block).max())
+    assert np.abs(block - steps).max() <= 2e-5 * max(scale, 1.0), np.abs(block - steps).max()
+    assert np.abs(block - mixed).max() <= 2e-5 * max(scale, 1.0), np.abs(block - mixed).max()
+    assert int(block.argmax()) == int(steps.argmax()) == int(mixed.argmax())
+    # and the mask matters: without it (prompt order permuted) the last position's logits change
+    other = om.decoder_forward_sequence(enc, [([p[1], p[0], p[2], p[3]], 0)])
+    assert np.abs(block - other).max() > 1e-3 * max(scale, 1.0)

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_chain_kernel(const __gri
     do {                                                                                                \
         if (P.dbg && blockIdx.x == 0 && lane == 0) P.dbg[CHAIN_MAX_PHASES * 3 * 8 + 504 + (k)] = ptx::globaltimer_ns(); \
     } while (0)
-    // Prologue, spread over the warps so that the CTA barrier falls ~0.5 us after the kernel starts (one thread walking
+    // Prologue, spread over the warps so that the CTA barrier falls ~0.9 us after the kernel starts (one thread walking
     // every phase's tensor maps and one warp computing the L2 prefetch ranges in front of the barrier took 2.2-2.7 us
     // per launch, nine launches per decode step: prologue timestamps in profiles/)
     if (warp == 3 && lane < P.n_phases && P.ph[lane].type == PH_GEMM) {  // lane p: the tensor maps of phase p

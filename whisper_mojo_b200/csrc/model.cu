@@ -572,7 +572,7 @@ static int build_chain_plans(Cache *c, Lane &ln) {
             }
         }
     }
-    // launch geometry + upload of the parameter blocks (allocates: build_chain_plans runs outside stream capture)
+    // launch geometry (grid, per-CTA L2 prefetch slices) once every phase is in place
     for (ChainPlan *p : ln.plans) WB_CHECK(chain_plan_finalize(p));
     WB_CHECK(chain_plan_finalize(ln.plan_last_nolog));
     return WB_OK;
@@ -585,8 +585,8 @@ static bool lane_is_fused(const Cache *c, const Lane &ln) {
     const bool want_fused = m->decode_fused == 1 || (m->decode_fused == 2 && ln.B <= FUSED_MAX_WAVE);
     return want_fused && m->gemm_impl == GEMM_IMPL_TC && (c->lanes.size() == 1 || fused_lanes) && m->D <= 768;
 }
-// Build the lanes' chain plans if the step will use them.  Allocates and copies, so every entry point calls it BEFORE
-// it queues / captures steps (greedy_loop, the step API, teacher forcing).
+// Build the lanes' chain plans if the step will use them.  Every entry point calls it BEFORE it queues / captures
+// steps (greedy_loop, the step API, teacher forcing), so nothing but launches happens inside a stream capture.
 static int prepare_chain_plans(Cache *c) {
     for (Lane &ln : c->lanes)
         if (lane_is_fused(c, ln) && ln.plans.empty()) WB_CHECK(build_chain_plans(c, ln));

@@ -19,7 +19,7 @@ tm = m.last_timing()
 print("eager + events run:", tm)
 tot = 0.0
 for k in ["cross_attention", "self_attention", "gemm_qkv", "gemm_o", "gemm_cross_q", "gemm_cross_o", "gemm_fc1", "gemm_fc2",
-          "layer_norm", "gemm_logits", "misc"]:
+          "layer_norm", "gemm_logits", "misc", "chain_first", "chain_b", "chain_ca"]:
     ms, n = m.last_kernel_timing(k)
     tot += ms
     print(f"{k:16s} {ms:8.2f} ms  {n:5d} launches  {1e3 * ms / max(n, 1):7.2f} us each")
